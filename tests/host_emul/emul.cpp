@@ -115,3 +115,99 @@ int emul_label(const uint8_t *mask, const uint8_t *markers, int h, int w, int ma
 }
 
 }  // extern "C"
+
+#include "../../ysmr_b200/csrc/link.cuh"
+
+struct HostLinkCta : HostCta {
+    void atomic_min_u64(unsigned long long *p, unsigned long long v) const { if (v < *p) *p = v; }
+    void atomic_min_i32(int32_t *p, int32_t v) const { if (v < *p) *p = v; }
+    void row_minima(const LinkConfig &c, const LinkState &s, const int32_t *order, int n, const float *dets, int m,
+                    double *row_min, int32_t *row_arg) const
+    {
+        row_minima_serial(*this, s, order, n, dets, m, row_min, row_arg);
+    }
+};
+
+struct HostLinker {
+    LinkConfig c;
+    LinkState s;
+    LinkScratch x;
+    std::vector<std::vector<double>> gains;
+    std::vector<int32_t> hdr, order0, order1, free_slots, id, gone, mode, hist_n, hist_pos, col_row, row_arg, list, table;
+    std::vector<double> px, py, hist, wgt, xh, row_min;
+    std::vector<float> iw, ih, ideg;
+    std::vector<unsigned long long> col_best;
+    std::vector<uint32_t> flag;
+};
+
+extern "C" {
+
+// gains: for each filter 4 x (2*n_i) row-major doubles, concatenated
+void *emul_link_create(double fps, int use_gsff, int n_f, const int32_t *n_i, const double *gain_full, int max_tracks,
+                       int max_blobs, double max_distance)
+{
+    HostLinker *L = new HostLinker();
+    LinkConfig &c = L->c;
+    c.max_disappeared = fps; c.max_distance = max_distance; c.use_gsff = use_gsff; c.n_f = n_f;
+    c.max_tracks = max_tracks; c.max_blobs = max_blobs;
+    c.cross_zero = 1;
+    const double *g = gain_full;
+    L->gains.resize(n_f);
+    for (int i = 0; i < n_f; ++i) {
+        c.n_i[i] = n_i[i];
+        const int n = n_i[i];
+        L->gains[i].resize(4 * n);
+        for (int k = 0; k < n; ++k) {
+            L->gains[i][k] = g[0 * 2 * n + 2 * k];
+            L->gains[i][n + k] = g[0 * 2 * n + 2 * k + 1];
+            L->gains[i][2 * n + k] = g[1 * 2 * n + 2 * k];
+            L->gains[i][3 * n + k] = g[1 * 2 * n + 2 * k + 1];
+            if (L->gains[i][n + k] != 0.0 || L->gains[i][2 * n + k] != 0.0) c.cross_zero = 0;
+        }
+        c.gain[i] = L->gains[i].data();
+        g += 4 * 2 * n;
+    }
+    c.hist_len = use_gsff ? c.n_i[n_f - 1] + 1 : 1;
+    const int T = max_tracks, B = max_blobs;
+    L->hdr.assign(8, 0); L->order0.resize(T); L->order1.resize(T); L->free_slots.resize(T);
+    L->id.assign(T, -1); L->gone.assign(T, 0); L->mode.assign(T, 0); L->hist_n.assign(T, 0); L->hist_pos.assign(T, 0);
+    L->px.resize(T); L->py.resize(T); L->iw.resize(T); L->ih.resize(T); L->ideg.resize(T);
+    L->hist.resize((size_t)T * c.hist_len * 2); L->wgt.resize((size_t)T * LINK_MAX_FILTERS); L->xh.resize((size_t)T * LINK_MAX_FILTERS * 2);
+    for (int i = 0; i < T; ++i) L->free_slots[i] = T - 1 - i;
+    L->hdr[2] = T;
+    LinkState &s = L->s;
+    s.hdr = L->hdr.data(); s.order[0] = L->order0.data(); s.order[1] = L->order1.data(); s.free_slots = L->free_slots.data();
+    s.id = L->id.data(); s.px = L->px.data(); s.py = L->py.data(); s.iw = L->iw.data(); s.ih = L->ih.data(); s.ideg = L->ideg.data();
+    s.gone = L->gone.data(); s.mode = L->mode.data(); s.hist_n = L->hist_n.data(); s.hist_pos = L->hist_pos.data();
+    s.hist = L->hist.data(); s.wgt = L->wgt.data(); s.xh = L->xh.data();
+    L->col_best.resize(B); L->col_row.resize(B); L->row_min.resize(T); L->row_arg.resize(T);
+    L->flag.resize((T > B ? T : B) + 2); L->list.resize(B); L->table.resize(set_table_capacity(B));
+    LinkScratch &x = L->x;
+    x.col_best = L->col_best.data(); x.col_row = L->col_row.data(); x.row_min = L->row_min.data(); x.row_arg = L->row_arg.data();
+    x.flag = L->flag.data(); x.list = L->list.data(); x.table = L->table.data(); x.set_table_size = (int)L->table.size();
+    return L;
+}
+
+void emul_link_destroy(void *h) { delete (HostLinker *)h; }
+
+// blob_count[n_frames], blobs[n_frames][max_blobs][5]; rows as 5 doubles? -> RowOut array.  Returns status bits.
+int emul_link_chunk(void *h, const int32_t *blob_count, const float *blobs, int first_frame, int n_frames, void *rows,
+                    long long rows_capacity, long long *n_rows)
+{
+    HostLinker *L = (HostLinker *)h;
+    int32_t status = 0, first_bad = 0x7fffffff;
+    LinkIo io;
+    io.blob_count = blob_count; io.blobs = blobs; io.rows = (RowOut *)rows; io.rows_capacity = rows_capacity;
+    io.n_rows = n_rows; io.append = 0; io.status = &status; io.first_bad = &first_bad;
+    HostLinkCta cta;
+    link_chunk(cta, L->c, L->s, L->x, io, first_frame, n_frames);
+    return status;
+}
+
+void emul_set_order(int32_t *keys, int n)
+{
+    std::vector<int32_t> table(set_table_capacity(n));
+    cpython_set_order(keys, n, table.data());
+}
+
+}  // extern "C"

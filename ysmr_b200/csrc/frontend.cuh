@@ -1,0 +1,33 @@
+// Parameters and launchers of the K1 front-end kernels (frontend.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace ysmr {
+
+struct FrontParams {
+    const uint8_t *frames;       // n_frames frames, H*W*channels bytes each
+    int64_t frame_stride;        // bytes between frames
+    int n_frames, h, w, ww, channels;
+    int t_mask, t_marker;        // d = blurred - mean;  BINARY: d > t ; BINARY_INV: d <= t  (== !(d > t))
+    int inverted;                // THRESH_BINARY_INV (dark bacteria)
+    const int32_t *scalar_thr;   // mean/std mode: per-frame threshold on the blurred image (NULL otherwise)
+    uint32_t *mask_bits;         // [n_frames][h][ww]
+    uint32_t *marker_bits;       // [n_frames][h][ww] or NULL (single threshold)
+    float k[11];                 // cv2.getGaussianKernel(11, 0, CV_32F)
+    int row_tail_from;           // w - w % 4 : first column of OpenCV's scalar tail of the row filter
+    int col_tail_from;           // w - w % 8 : first column of the scalar tail of the column filter
+    // optional byte-image dumps [n_frames][h][w] (tile kernel only)
+    uint8_t *dbg_grey, *dbg_blurred, *dbg_mean;
+};
+
+cudaError_t launch_frontend_tile(const FrontParams &p, cudaStream_t st);
+cudaError_t launch_frontend_strip(const FrontParams &p, cudaStream_t st);
+cudaError_t launch_unpack_bits(const uint32_t *bits, uint8_t *bytes, int64_t rows, int w, int ww, cudaStream_t st);
+cudaError_t launch_frame_moments(const uint8_t *frames, int64_t stride, int n_frames, int h, int w, int channels,
+                                 unsigned long long *sums, cudaStream_t st);
+cudaError_t launch_moving_threshold(const unsigned long long *sums, int n_frames, int h, int w, int white_on_dark,
+                                    int signed_offset, int first_frame, int window, double *values, int32_t *thr,
+                                    cudaStream_t st);
+
+}  // namespace ysmr

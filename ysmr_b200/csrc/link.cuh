@@ -1,0 +1,411 @@
+// K4/K5 -- the sequential linker: nearest-neighbour association with disappearance counters and the in-loop
+// Gaussian-sum FIR filter.
+//
+// Replaces CentroidTracker.update (/root/reference/ysmr/tracker.py:93-230) -- including scipy's cdist (tracker.py:151),
+// the row-min argsort greedy match (158-189), the two asymmetric branches (198-217) and CPython's set iteration order
+// for several births in one frame (193, 216-217) -- and GaussianSumFIR.correct/predict (/root/reference/ysmr/
+// gsff.py:204-347), plus the row append of the loop (track_eval.py:313-316).  Data-parallel restatement:
+// `rows` of the reference is a permutation, so "row in used_rows" never fires and the greedy loop reduces to: every
+// detection is won by the track with the smallest row-minimum among the tracks whose nearest detection it is.
+//
+// One CTA walks the frames of a chunk in order; within a frame the phases below are loops over tracks/detections
+// separated by cta.sync().  The Cta policy supplies barrier, scan and atomics (device: link.cu; host emulation for
+// the CPU test-suite: tests/host_emul).  All association and filter arithmetic is float64 like the reference.
+#pragma once
+#include "common.cuh"
+
+#if !defined(__CUDA_ARCH__)
+#include <math.h>
+#endif
+
+namespace ysmr {
+
+constexpr int LINK_MAX_FILTERS = 4;
+constexpr int LINK_MAX_HORIZON = 64;
+
+struct LinkConfig {
+    double max_disappeared;              // = fps (tracker.py:42, track_eval.py:110)
+    double max_distance;                 // <= 0: no gate (reference behaviour)
+    int use_gsff, n_f;
+    int n_i[LINK_MAX_FILTERS];           // horizons (gsff.py:103-109)
+    int hist_len;                        // n_i[n_f-1] + 1 (gsff.py:317-318)
+    int cross_zero;                      // 1: the x<-y / y<-x gain entries are all exactly zero
+    // gains, device memory: for filter i four arrays of n_i[i] doubles: xx, xy, yx, yy
+    //   x_hat = sum_k xx[k]*mx[k] + xy[k]*my[k] ; y_hat = sum_k yx[k]*mx[k] + yy[k]*my[k]
+    const double *gain[LINK_MAX_FILTERS];
+    int max_tracks, max_blobs;
+};
+
+// Persistent linker state (device memory).  Tracks live in physical slots; `order` lists the slots in insertion order
+// (the reference's OrderedDict order), so deregistration only compacts `order`.
+struct LinkState {
+    int32_t *hdr;                        // [8]: n_tracks, next_id, n_free, order_sel, frames_done, last_n_live
+    int32_t *order[2];                   // [max_tracks] ping-pong
+    int32_t *free_slots;                 // [max_tracks] stack of free physical slots
+    int32_t *id;                         // per slot ...
+    double *px, *py;                     //   position used for the next association (GSFF prediction)
+    float *iw, *ih, *ideg;               //   additional_info (w, h, deg) or zeros
+    int32_t *gone;                       //   consecutive misses
+    int32_t *mode, *hist_n, *hist_pos;   //   GSFF: active filters, valid history entries, ring write position
+    double *hist;                        //   [slot][hist_len][2]
+    double *wgt;                         //   [slot][LINK_MAX_FILTERS]
+    double *xh;                          //   [slot][LINK_MAX_FILTERS][2]
+};
+
+// Per-frame scratch (device: global memory owned by the context).
+struct LinkScratch {
+    unsigned long long *col_best;        // [max_blobs] bits of the smallest row-minimum that chose this detection
+    int32_t *col_row;                    // [max_blobs] winning row
+    double *row_min;                     // [max_tracks]
+    int32_t *row_arg;                    // [max_tracks]
+    uint32_t *flag;                      // [max(max_tracks, max_blobs) + 1] scan buffer
+    int32_t *list;                       // [max_blobs] unused detections ascending, then in registration order
+    int32_t *table;                      // [set_table_size] CPython set emulation
+    int set_table_size;
+};
+
+struct RowOut {                          // must match ysmr_row (include/ysmr_b200.h)
+    int32_t frame, track_id;
+    double x, y;
+    float w, h, deg;
+    int32_t pad;
+};
+
+enum { LINK_ST_TRACK_OVERFLOW = 8, LINK_ST_ROW_OVERFLOW = 16 };
+
+YSMR_HD unsigned long long f64_bits(double v)
+{
+#if defined(__CUDA_ARCH__)
+    return (unsigned long long)__double_as_longlong(v);
+#else
+    unsigned long long u; memcpy(&u, &v, 8); return u;
+#endif
+}
+
+// ---- CPython 3.12 set iteration order of {keys inserted ascending}; SURVEY A.10 / oracle/setorder.py ---------------
+// keys[0..n) ascending on entry, registration order on exit.  table: scratch of >= set_table_capacity(n) ints.
+YSMR_HD int set_table_capacity(int n)
+{
+    int size = 8;
+    while (size <= 4 * n) size <<= 1;   // the largest table ever built for n keys ...
+    return 2 * size;                    // ... plus room for the rebuild (old table in front of the new one)
+}
+
+YSMR_HD void set_insert(int32_t *table, int mask, int key)
+{
+    unsigned perturb = (unsigned)key;
+    int i = key & mask;
+    for (;;) {
+        const int last = (i + 9 <= mask) ? i + 9 : i;
+        for (int j = i; j <= last; ++j)
+            if (table[j] < 0) { table[j] = key; return; }
+        perturb >>= 5;
+        i = (int)(((unsigned)i * 5u + 1u + perturb) & (unsigned)mask);
+    }
+}
+
+YSMR_HD void cpython_set_order(int32_t *keys, int n, int32_t *table)
+{
+    if (n <= 1) return;
+    int mask = 7, fill = 0;
+    for (int j = 0; j <= mask; ++j) table[j] = -1;
+    for (int q = 0; q < n; ++q) {
+        set_insert(table, mask, keys[q]);
+        ++fill;
+        if (fill * 5 >= mask * 3) {
+            const int want = fill > 50000 ? fill * 2 : fill * 4;
+            int size = 8;
+            while (size <= want) size <<= 1;
+            // rebuild: the old entries are re-inserted in old slot order.  Old table occupies [0, mask]; build the new
+            // one behind it, then move it to the front.
+            int32_t *nt = table + (mask + 1);
+            for (int j = 0; j < size; ++j) nt[j] = -1;
+            for (int j = 0; j <= mask; ++j)
+                if (table[j] >= 0) set_insert(nt, size - 1, table[j]);
+            for (int j = 0; j < size; ++j) table[j] = nt[j];
+            mask = size - 1;
+        }
+    }
+    int k = 0;
+    for (int j = 0; j <= mask; ++j)
+        if (table[j] >= 0) keys[k++] = table[j];
+}
+
+// ---- GSFF (gsff.py) for one track ----------------------------------------------------------------------------------
+
+YSMR_HD void gsff_estimates(const LinkConfig &c, const LinkState &s, int slot, int mode)
+{
+    const double *hist = s.hist + (int64_t)slot * c.hist_len * 2;
+    const int pos = s.hist_pos[slot];
+    for (int i = 0; i < mode; ++i) {
+        const int n = c.n_i[i];
+        const double *g = c.gain[i];
+        double ax = 0.0, ay = 0.0;
+        int j = pos - n; if (j < 0) j += c.hist_len;
+        for (int k = 0; k < n; ++k) {
+            const double mx = hist[2 * j], my = hist[2 * j + 1];
+            if (c.cross_zero) {
+                ax = fma(g[k], mx, ax);
+                ay = fma(g[3 * n + k], my, ay);
+            } else {
+                ax = fma(g[k], mx, ax); ax = fma(g[n + k], my, ax);
+                ay = fma(g[2 * n + k], mx, ay); ay = fma(g[3 * n + k], my, ay);
+            }
+            if (++j == c.hist_len) j = 0;
+        }
+        s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2] = ax;
+        s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2 + 1] = ay;
+    }
+}
+
+YSMR_HD void gsff_push(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy)
+{
+    double *hist = s.hist + (int64_t)slot * c.hist_len * 2;
+    int pos = s.hist_pos[slot];
+    hist[2 * pos] = zx; hist[2 * pos + 1] = zy;
+    if (++pos == c.hist_len) pos = 0;
+    s.hist_pos[slot] = pos;
+    if (s.hist_n[slot] < c.hist_len) s.hist_n[slot] += 1;
+}
+
+// correct() then predict() for one track (tracker.py:221-225).  (zx, zy) = self.objects[key]; out = filtered position
+// written to the CSV; the stored position becomes the prediction.
+YSMR_HD void gsff_step(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy, double *ox, double *oy)
+{
+    if (s.hist_n[slot] == 0) {                       // first call: previous_measurements = [z] * n_i[0]
+        for (int k = 0; k < c.n_i[0]; ++k) gsff_push(c, s, slot, zx, zy);
+    }
+    int mode = s.mode[slot];
+    bool switched = false;
+    if (mode < c.n_f) {
+        while (s.hist_n[slot] >= c.n_i[mode]) {
+            ++mode; switched = true;
+            if (mode >= c.n_f) break;
+        }
+    }
+    double *w = s.wgt + (int64_t)slot * LINK_MAX_FILTERS;
+    double *xh = s.xh + (int64_t)slot * LINK_MAX_FILTERS * 2;
+    if (switched) {
+        s.mode[slot] = mode;
+        const double w0 = 1.0 / (double)mode;
+        for (int i = 0; i < mode; ++i) w[i] = w0;
+        gsff_estimates(c, s, slot, mode);
+    }
+    double lik[LINK_MAX_FILTERS];
+    double total = 0.0;
+    for (int i = 0; i < mode; ++i) {
+        const double dx = zx - xh[2 * i], dy = zy - xh[2 * i + 1];
+        double v = exp(-0.5 * (dx * dx + dy * dy));
+        if (v < 1e-20) v = 1e-20;
+        lik[i] = v;
+        total = total + v * w[i];
+    }
+    gsff_push(c, s, slot, zx, zy);
+    double fx = 0.0, fy = 0.0;
+    for (int i = 0; i < mode; ++i) {
+        w[i] = lik[i] * w[i] / total;
+        if (i == 0) { fx = xh[0] * w[0]; fy = xh[1] * w[0]; }
+        else { fx = fx + xh[2 * i] * w[i]; fy = fy + xh[2 * i + 1] * w[i]; }
+    }
+    *ox = fx; *oy = fy;
+    gsff_estimates(c, s, slot, mode);
+    double qx = 0.0, qy = 0.0;
+    for (int i = 0; i < mode; ++i) {
+        if (i == 0) { qx = xh[0] * w[0]; qy = xh[1] * w[0]; }
+        else { qx = qx + xh[2 * i] * w[i]; qy = qy + xh[2 * i + 1] * w[i]; }
+    }
+    s.px[slot] = qx; s.py[slot] = qy;
+}
+
+// ---- one frame -------------------------------------------------------------------------------------------------------
+
+struct LinkIo {
+    const int32_t *blob_count;           // [n_frames]
+    const float *blobs;                  // [n_frames][max_blobs][5]
+    RowOut *rows;
+    long long rows_capacity;
+    long long *n_rows;                   // [1] rows written (append == 0) or running total (append == 1)
+    int append;                          // 1: start writing at rows[*n_rows] and add to it (chunked pipelines)
+    int32_t *status;                     // [1]
+    int32_t *first_bad;                  // [1] lowest frame that overflowed, or -1
+};
+
+template <class Cta>
+YSMR_HD void link_init_track(const LinkConfig &c, const LinkState &s, int slot, int id, const float *det)
+{
+    s.id[slot] = id;
+    s.px[slot] = (double)det[0]; s.py[slot] = (double)det[1];
+    s.iw[slot] = det[2]; s.ih[slot] = det[3]; s.ideg[slot] = det[4];
+    s.gone[slot] = 0;
+    s.mode[slot] = 0; s.hist_n[slot] = 0; s.hist_pos[slot] = 0;
+}
+
+// Processes frames [0, n_frames) of the chunk.  Header values live in registers of every thread and are updated
+// identically by all of them (every quantity they depend on is CTA-uniform), thread 0 writes them back at the end.
+template <class Cta>
+YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const LinkScratch &x, const LinkIo &io,
+                        int first_frame, int n_frames)
+{
+    const int tid = cta.tid(), nthr = cta.nthr();
+    int n = s.hdr[0], next_id = s.hdr[1], n_free = s.hdr[2], sel = s.hdr[3];
+    long long rows_total = io.append ? *io.n_rows : 0;
+    bool row_overflow = false;
+
+    for (int fi = 0; fi < n_frames; ++fi) {
+        const int m = io.blob_count[fi];
+        const float *dets = io.blobs + (int64_t)fi * c.max_blobs * 5;
+        int32_t *order = s.order[sel];
+        bool age_unmatched = false;      // rows with flag[r] == 0 are aged afterwards
+        int births = 0;
+
+        if (m == 0) {
+            for (int r = tid; r < n; r += nthr) x.flag[r] = 0;              // nobody matched
+            age_unmatched = true;
+            cta.sync();
+        } else if (n == 0) {
+            births = m;
+            for (int q = tid; q < m; q += nthr) x.list[q] = q;              // detection order (tracker.py:135-137)
+            cta.sync();
+        } else {
+            for (int q = tid; q < m; q += nthr) { x.col_best[q] = ~0ull; x.col_row[q] = 0x7fffffff; }
+            cta.sync();
+            // nearest detection of every track (cdist row minimum / first argmin, tracker.py:151-163)
+            cta.row_minima(c, s, order, n, dets, m, x.row_min, x.row_arg);
+            cta.sync();
+            for (int r = tid; r < n; r += nthr) {
+                const double d = x.row_min[r];
+                if (c.max_distance <= 0.0 || d <= c.max_distance) cta.atomic_min_u64(&x.col_best[x.row_arg[r]], f64_bits(d));
+            }
+            cta.sync();
+            for (int r = tid; r < n; r += nthr) {
+                const int q = x.row_arg[r];
+                if (x.col_best[q] == f64_bits(x.row_min[r]) && (c.max_distance <= 0.0 || x.row_min[r] <= c.max_distance))
+                    cta.atomic_min_i32(&x.col_row[q], r);
+            }
+            cta.sync();
+            for (int r = tid; r < n; r += nthr) {
+                const int q = x.row_arg[r];
+                const bool won = x.col_row[q] == r;
+                x.flag[r] = won ? 1u : 0u;
+                if (won) {                                                  // tracker.py:181-184
+                    const int slot = order[r];
+                    const float *d = dets + 5 * q;
+                    s.px[slot] = (double)d[0]; s.py[slot] = (double)d[1];
+                    s.iw[slot] = d[2]; s.ih[slot] = d[3]; s.ideg[slot] = d[4];
+                    s.gone[slot] = 0;
+                }
+            }
+            cta.sync();
+            if (n >= m) {
+                age_unmatched = true;                                       // tracker.py:198-211
+            } else {                                                        // tracker.py:215-217
+                for (int q = tid; q <= m; q += nthr) x.flag[q] = (q < m && x.col_row[q] == 0x7fffffff) ? 1u : 0u;
+                cta.sync();
+                births = (int)cta.exclusive_scan(x.flag, m + 1);
+                for (int q = tid; q < m; q += nthr)
+                    if (x.flag[q + 1] != x.flag[q]) x.list[x.flag[q]] = q;  // unused detections, ascending
+                cta.sync();
+                if (tid == 0) cpython_set_order(x.list, births, x.table);
+                cta.sync();
+            }
+        }
+
+        if (age_unmatched) {
+            // flag[r] = 1 matched.  Age the others, drop those beyond max_disappeared, compact `order`.
+            for (int r = tid; r < n; r += nthr) {
+                uint32_t keep = 1;
+                if (!x.flag[r]) {
+                    const int slot = order[r];
+                    const int g = s.gone[slot] + 1;
+                    s.gone[slot] = g;
+                    s.iw[slot] = 0.f; s.ih[slot] = 0.f; s.ideg[slot] = 0.f;   // [0] * len(info)
+                    if ((double)g > c.max_disappeared) keep = 0;
+                }
+                x.flag[r] = keep;
+            }
+            if (tid == 0) x.flag[n] = 0;
+            cta.sync();
+            const int kept = (int)cta.exclusive_scan(x.flag, n + 1);
+            if (kept != n) {
+                int32_t *order2 = s.order[sel ^ 1];
+                for (int r = tid; r < n; r += nthr) {
+                    const int before = (int)x.flag[r];
+                    if ((int)x.flag[r + 1] != before) order2[before] = order[r];
+                    else s.free_slots[n_free + (r - before)] = order[r];
+                }
+                cta.sync();
+                n_free += n - kept;
+                n = kept;
+                sel ^= 1;
+                order = s.order[sel];
+            }
+        }
+        if (births > 0) {
+            int room = c.max_tracks - n;
+            if (births > room) {
+                if (tid == 0) { cta.atomic_or_i32(io.status, LINK_ST_TRACK_OVERFLOW); cta.atomic_min_i32(io.first_bad, first_frame + fi); }
+                births = room;
+            }
+            for (int b = tid; b < births; b += nthr) {
+                const int slot = s.free_slots[n_free - 1 - b];
+                order[n + b] = slot;
+                link_init_track<Cta>(c, s, slot, next_id + b, dets + 5 * x.list[b]);
+            }
+            cta.sync();
+            n += births; next_id += births; n_free -= births;
+        }
+
+        // filter + emit (tracker.py:219-227, track_eval.py:313-316)
+        const bool room = rows_total + n <= io.rows_capacity;
+        for (int r = tid; r < n; r += nthr) {
+            const int slot = order[r];
+            double ox = s.px[slot], oy = s.py[slot];
+            if (c.use_gsff) gsff_step(c, s, slot, ox, oy, &ox, &oy);
+            if (room) {
+                RowOut &o = io.rows[rows_total + r];
+                o.frame = first_frame + fi; o.track_id = s.id[slot];
+                o.x = ox; o.y = oy; o.w = s.iw[slot]; o.h = s.ih[slot]; o.deg = s.ideg[slot]; o.pad = 0;
+            }
+        }
+        if (room) rows_total += n;
+        else if (!row_overflow) {
+            row_overflow = true;
+            if (tid == 0) { cta.atomic_or_i32(io.status, LINK_ST_ROW_OVERFLOW); cta.atomic_min_i32(io.first_bad, first_frame + fi); }
+        }
+        cta.sync();
+    }
+    if (tid == 0) {
+        s.hdr[0] = n; s.hdr[1] = next_id; s.hdr[2] = n_free; s.hdr[3] = sel;
+        s.hdr[4] += n_frames; s.hdr[5] = n;
+        *io.n_rows = rows_total;
+    }
+}
+
+// Row minima, generic one-thread-per-track form (the device policy overrides it with a multi-lane version).
+// scipy's euclidean: s = 0; s += d*d per coordinate (separately rounded); sqrt(s).  argmin = first index of the minimum
+// of the ROUNDED distances, so candidates whose squared distance is within a few ulp of the minimum are compared after
+// the square root.
+template <class Cta>
+YSMR_HD void row_minima_serial(const Cta &cta, const LinkState &s, const int32_t *order, int n, const float *dets, int m,
+                               double *row_min, int32_t *row_arg)
+{
+    for (int r = cta.tid(); r < n; r += cta.nthr()) {
+        const int slot = order[r];
+        const double ox = s.px[slot], oy = s.py[slot];
+        double best = 0.0; int arg = 0;
+        for (int q = 0; q < m; ++q) {
+            const double dx = ox - (double)dets[5 * q], dy = oy - (double)dets[5 * q + 1];
+            const double d = sqrt(dx * dx + dy * dy);
+            if (q == 0 || d < best) { best = d; arg = q; }
+        }
+        row_min[r] = best; row_arg[r] = arg;
+    }
+}
+
+#if defined(__CUDACC__)
+cudaError_t launch_link(const LinkConfig &c, const LinkState &s, const LinkScratch &x, const LinkIo &io, int first_frame,
+                        int n_frames, cudaStream_t st);
+cudaError_t launch_link_reset(const LinkState &s, int max_tracks, cudaStream_t st);
+#endif
+
+}  // namespace ysmr
