@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- frames/s of the detect + link (+GSFF) hot path at 1228x922 on N B200s, with the HBM roofline of the
+dominant kernel and the reference's CPU path timed beside it.
+
+Contract (one JSON line on stdout from rank 0):
+  python bench.py --gpus N --steps K --warmup W            # ours
+  python bench.py --impl reference --gpus N --steps K ...  # the reference's CPU implementation of the same path
+
+Workload at N=1: BASELINE.json configs[1] -- the cfg1 scene (1228x922, ~50 rod-shaped bacteria, default tracking.ini)
+continued to 9,000 frames, BGR frames as cap.read() delivers them, resident in HBM.  A "step" is one pass of
+detect+link+gsff over the whole 9,000-frame video (30.6 GB of input, far larger than L2).  At N>1 every rank holds its
+own 9,000-frame range of an N*9,000-frame video (weak scaling); detections are gathered over NCCL and linked by the one
+sequential linker on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--frames', type=int, default=9000, help='frames per GPU (configs[1]: 9000)')
+    ap.add_argument('--channels', type=int, default=3, choices=[1, 3])
+    ap.add_argument('--cells', type=int, default=50)
+    ap.add_argument('--batch', type=int, default=256, help='frames per detect launch')
+    ap.add_argument('--cpu-frames', type=int, default=300, help='frames of the bounded CPU sample')
+    ap.add_argument('--e2e-frames', type=int, default=1000, help='frames in the pinned host buffer of the e2e leg')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--no-cpu', action='store_true')
+    return ap.parse_args()
+
+
+# ---- clocks ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, gpu_index=0):
+        self.path = os.path.join(tempfile.gettempdir(), f'ysmr_clocks_{os.getpid()}.csv')
+        self.proc = None
+        self.gpu = gpu_index
+
+    def start(self):
+        try:
+            self.fh = open(self.path, 'w')
+            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100'], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            p = [x.strip() for x in line.split(',')]
+            if len(p) < 9:
+                continue
+            try:
+                sm.append(float(p[1])); mx.append(float(p[2]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        if sm:
+            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
+                   'samples': len(sm)}
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        return out
+
+
+# ---- CPU baseline: the reference's loop body (oracle = cv2/scipy call sites + restated linker) ---------------------------
+def cpu_reference_fps(frames_bgr_or_grey, fps=30.0):
+    """Replays track_eval.py:180-316 on in-RAM frames (oracle/; the reference itself cannot travel to the GPU box)."""
+    import cv2
+    from oracle import ref_stages
+    from oracle.tracker_port import LinkerPort
+    st = ref_stages.DetectSettings()
+    lp = LinkerPort(max_disappeared=fps, fps=fps)
+    t0 = time.perf_counter()
+    n_rows = 0
+    for f in frames_bgr_or_grey:
+        r = ref_stages.detect_frame(f, st)
+        n_rows += len(lp.update(r['rects']))
+    dt = time.perf_counter() - t0
+    return len(frames_bgr_or_grey) / dt, dt, n_rows, cv2.getNumThreads()
+
+
+def scene_for(args, n_total):
+    from ysmr_b200.synth import SceneConfig, make_scene
+    return make_scene(SceneConfig(n_frames=n_total, n_cells=args.cells, seed=0))
+
+
+def run_reference(args):
+    """--impl reference: rank 0 only; each step is a bounded sample (args.cpu_frames frames) of the same workload."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from ysmr_b200.synth import render_frames, to_bgr
+    n = args.cpu_frames
+    scene = scene_for(args, n)
+    grey = render_frames(scene, 0, n)
+    frames = to_bgr(grey) if args.channels == 3 else grey
+    for _ in range(min(args.warmup, 1)):
+        cpu_reference_fps(frames[:30])
+    vals, secs = [], []
+    for _ in range(args.steps):
+        fps, dt, _, threads = cpu_reference_fps(frames)
+        vals.append(fps); secs.append(dt)
+    v = float(np.mean(vals))
+    line = {
+        'impl': 'reference', 'metric': 'frames/sec detect+link at 1228x922', 'value': v, 'unit': 'frames/s',
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(secs) * 1000),
+        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32/f64', 'data': 'synthetic',
+        'config': {'workload': f'cfg2 scene: 1228x922x{args.channels}, {args.cells} rods, default tracking.ini; '
+                               f'CPU sample = first {n} frames per step, frames in RAM'},
+        'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+                         'sample': f'{n} frames/step x {args.steps} steps; oracle = the reference loop body '
+                                   f'(track_eval.py:180-316) on cv2/scipy + restated CentroidTracker/GSFF; '
+                                   f'host has {os.cpu_count()} cpus'},
+        'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from ysmr_b200.api import ROW_DTYPE, Context
+    from ysmr_b200.synth import render_frames_torch
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local = int(os.environ.get('LOCAL_RANK', '0'))
+    assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+
+    H, W, Cn, F = 922, 1228, args.channels, args.frames
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
+    peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
+
+    # ---- synthetic video of world*F frames; this rank renders and keeps frames [rank*F, (rank+1)*F) in HBM ------------
+    scene = scene_for(args, world * F)
+    shape = (F, H, W) if Cn == 1 else (F, H, W, 3)
+    frames = torch.empty(shape, dtype=torch.uint8, device=dev)
+    G = 200
+    for a in range(0, F, G):
+        b = min(F, a + G)
+        render_frames_torch(scene, rank * F + a, rank * F + b, dev, channels=Cn, out=frames[a:b])
+    torch.cuda.synchronize()
+
+    MB, MT = 512, 1024
+    ctx = Context(H, W, Cn, local, max_batch=args.batch, max_blobs=MB, max_tracks=MT)
+    rows_cap = world * F * 160
+    rows_buf = torch.empty(rows_cap * ROW_DTYPE.itemsize, dtype=torch.uint8, device=dev) if rank == 0 else None
+
+    def step_single():
+        ctx.reset()
+        return ctx.track_device(frames, 0, rows_capacity=rows_cap, rows_buf=rows_buf, return_device=True)
+
+    # multi-GPU: every rank detects its frame range; detections go to rank 0 which links all ranges in frame order
+    KEEP = 128            # detections per frame that travel (count is checked against it)
+    def step_multi():
+        counts = torch.empty(F, dtype=torch.int32, device=dev)
+        blobs = torch.empty((F, KEEP, 5), dtype=torch.float32, device=dev)
+        for a in range(0, F, args.batch):
+            b = min(F, a + args.batch)
+            c, bl = ctx.detect(frames[a:b], rank * F + a)
+            counts[a:b] = c; blobs[a:b] = bl[:, :KEEP]
+        gc = [torch.empty_like(counts) for _ in range(world)] if rank == 0 else None
+        gb = [torch.empty_like(blobs) for _ in range(world)] if rank == 0 else None
+        dist.gather(counts, gc, dst=0)
+        dist.gather(blobs, gb, dst=0)
+        if rank == 0:
+            ctx.reset()
+            if not hasattr(step_multi, 'lctx'):
+                step_multi.lctx = Context(H, W, Cn, local, max_batch=8, max_blobs=KEEP, max_tracks=MT)
+            l = step_multi.lctx
+            l.reset()
+            n_rows = torch.zeros(1, dtype=torch.int64, device=dev)
+            total = 0
+            for r in range(world):
+                assert int(gc[r].max()) <= KEEP
+                # ysmr_link appends nothing across calls; rows of successive ranges go to successive slices
+                import ctypes as C
+                nr = torch.zeros(1, dtype=torch.int64, device=dev)
+                off = total * ROW_DTYPE.itemsize
+                l._check(l.lib.ysmr_link(l._h, C.c_void_p(gc[r].data_ptr()), C.c_void_p(gb[r].data_ptr()), r * F, F,
+                                         C.c_void_p(rows_buf.data_ptr() + off), rows_cap - total,
+                                         C.c_void_p(nr.data_ptr()), l._stream_ptr()))
+                total += int(nr.item())
+            n_rows[0] = total
+            return rows_buf, n_rows
+        return None, None
+
+    step = step_single if world == 1 else step_multi
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    ctx.set_profiling(True)
+    launches0 = ctx.launch_count()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        rows_dev, n_rows_dev = step()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    launches = ctx.launch_count() - launches0
+    if world > 1 and rank == 0 and hasattr(step_multi, 'lctx'):
+        launches += step_multi.lctx.launch_count()
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    if rank != 0:
+        if world > 1:
+            dist.barrier()
+            dist.destroy_process_group()
+        return
+
+    total_frames = world * F * args.steps
+    value = total_frames / (ms / 1000.0)
+    n_rows = int(n_rows_dev.item())
+    rows = rows_dev[:n_rows * ROW_DTYPE.itemsize].cpu().numpy().view(ROW_DTYPE)
+    n_tracks = int(rows['track_id'].max()) + 1 if n_rows else 0
+
+    # ---- roofline of the dominant kernel (front-end): algorithmic bytes = H*W*C per frame, frames/launch ----
+    fe_ms, fe_n = prof['frontend']
+    bytes_per_frame = H * W * Cn
+    frames_per_launch = (F * args.steps) / max(fe_n, 1)
+    achieved = (bytes_per_frame * frames_per_launch) / (fe_ms / max(fe_n, 1) / 1000.0) / 1e9 if fe_ms > 0 else 0.0
+    roofline = {'bound': 'hbm', 'kernel': 'frontend (K1)', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
+                'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
+                'algorithmic_bytes_per_frame': bytes_per_frame, 'frames_per_launch': frames_per_launch,
+                'avg_launch_ms': fe_ms / max(fe_n, 1),
+                'kernel_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
+                'whole_path_frac': (value * bytes_per_frame / 1e9) / (hbm_peak * world)}
+
+    # ---- e2e: the same metric through ysmr_track_host with pinned HOST frames (H2D + kernels + D2H rows inside) ---------
+    e2e = None
+    if not args.no_e2e and world == 1:
+        E = min(args.e2e_frames, F)
+        host = torch.empty((E,) + shape[1:], dtype=torch.uint8).pin_memory()
+        host.copy_(frames[:E])
+        host_np = host.numpy()
+        rows_out = np.empty(E * 160, ROW_DTYPE)
+        calls = (F + E - 1) // E
+        def e2e_step():
+            ctx.reset()
+            got = 0
+            for c in range(calls):
+                got += len(ctx.track_host(host_np, c * E, rows_capacity=len(rows_out), rows_out=rows_out))
+            return got
+        e2e_step()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = 0
+        for _ in range(args.steps):
+            got = e2e_step()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e = {'value': calls * E * args.steps / dt, 'unit': 'frames/s',
+               'h2d_bytes_per_step': calls * E * bytes_per_frame, 'd2h_bytes_per_step': got * ROW_DTYPE.itemsize,
+               'note': f'ysmr_track_host on a pinned {E}-frame buffer x {calls} calls per step; wall clock incl. H2D, '
+                       f'kernels, D2H of rows'}
+
+    # ---- CPU baseline on a bounded sample of the same bytes ---------------------------------------------------------------
+    cpu = None
+    if not args.no_cpu and world == 1:
+        S = min(args.cpu_frames, F)
+        sample = frames[:S].cpu().numpy()
+        fps_cpu, dt_cpu, _, threads = cpu_reference_fps(sample)
+        cpu = {'value': fps_cpu, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
+               'sample': f'first {S} frames of the same video, {dt_cpu:.1f} s; reference loop body (track_eval.py:180-316) '
+                         f'replayed on cv2/scipy + restated CentroidTracker/GSFF; host has {os.cpu_count()} cpus'}
+
+    line = {
+        'metric': 'frames/sec detect+link at 1228x922', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+        'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32/f64', 'data': 'synthetic',
+        'config': {'workload': f'cfg2: 1228x922x{Cn} (BGR as cap.read() delivers) x {F} frames per GPU, {args.cells} rods, '
+                               f'default tracking.ini (white-on-dark, offset 5, adaptive double threshold 2.0, gsff 10/20/30)',
+                   'frames_per_gpu': F, 'batch': args.batch, 'l2': 'inputs (>= 10 GB) far exceed the 126 MB L2',
+                   'parallelism': f'frame-range x{world}, one sequential linker', 'rows': n_rows, 'tracks': n_tracks},
+        'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

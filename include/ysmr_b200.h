@@ -155,6 +155,13 @@ int ysmr_track_device(ysmr_ctx *ctx, const uint8_t *d_frames, int n_frames, int6
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches claim). */
 int64_t ysmr_launch_count(const ysmr_ctx *ctx);
 
+/* Per-kernel timing for bench.py's roofline: when enabled every kernel launch is bracketed by CUDA events on the stream
+ * it is launched on.  ysmr_get_profile synchronises, writes the summed milliseconds and the number of launches per
+ * kernel kind (arrays of YSMR_PROF_KINDS entries) and clears the record. */
+enum { YSMR_PROF_FRONTEND = 0, YSMR_PROF_LABEL = 1, YSMR_PROF_GEOMETRY = 2, YSMR_PROF_LINK = 3, YSMR_PROF_KINDS = 4 };
+int ysmr_set_profiling(ysmr_ctx *ctx, int enabled);
+int ysmr_get_profile(ysmr_ctx *ctx, double *ms, int64_t *launches);
+
 #ifdef __cplusplus
 }
 #endif

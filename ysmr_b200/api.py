@@ -208,3 +208,14 @@ class Context:
 
     def launch_count(self):
         return int(self.lib.ysmr_launch_count(self._h))
+
+    PROF_KINDS = ('frontend', 'label', 'geometry', 'link')
+
+    def set_profiling(self, enabled=True):
+        self._check(self.lib.ysmr_set_profiling(self._h, int(bool(enabled))))
+
+    def get_profile(self):
+        """{kind: (total_ms, launches)} since the last call; synchronises the device."""
+        ms = (C.c_double * 4)(); n = (C.c_int64 * 4)()
+        self._check(self.lib.ysmr_get_profile(self._h, ms, n))
+        return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_KINDS)}

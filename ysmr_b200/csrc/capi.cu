@@ -75,6 +75,10 @@ struct ysmr_ctx {
     ysmr_row *rows_dev = nullptr; int64_t rows_dev_cap = 0;
     long long *n_rows_dev = nullptr;
     std::vector<void *> allocs;
+    // optional per-kernel timing (ysmr_set_profiling): event pairs recorded around every launch on its own stream
+    int profiling = 0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_events[YSMR_PROF_KINDS];
+    std::vector<cudaEvent_t> prof_free;
 };
 
 namespace {
@@ -100,6 +104,26 @@ cudaError_t dev_alloc(ysmr_ctx *c, T **out, size_t count)
     if (e == cudaSuccess) { c->allocs.push_back(p); *out = (T *)p; }
     return e;
 }
+
+cudaEvent_t prof_event(ysmr_ctx *c)
+{
+    cudaEvent_t e = nullptr;
+    if (!c->prof_free.empty()) { e = c->prof_free.back(); c->prof_free.pop_back(); }
+    else cudaEventCreate(&e);
+    return e;
+}
+
+struct ProfScope {          // records start now and stop at scope exit on `st`, filed under `kind`
+    ysmr_ctx *c; int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+    ProfScope(ysmr_ctx *c_, int kind_, cudaStream_t st_) : c(c_), kind(kind_), st(st_)
+    {
+        if (c->profiling) { a = prof_event(c); b = prof_event(c); cudaEventRecord(a, st); }
+    }
+    ~ProfScope()
+    {
+        if (a) { cudaEventRecord(b, st); c->prof_events[kind].push_back({a, b}); }
+    }
+};
 
 int derive_thresholds(ysmr_ctx *c)
 {
@@ -264,6 +288,9 @@ int ysmr_destroy(ysmr_ctx *c)
     cudaSetDevice(c->device);
     cudaDeviceSynchronize();
     for (void *p : c->allocs) cudaFree(p);
+    for (int k = 0; k < YSMR_PROF_KINDS; ++k)
+        for (auto &pr : c->prof_events[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
+    for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
     if (c->rows_dev) cudaFree(c->rows_dev);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFree(c->stage[i]);
@@ -326,7 +353,10 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
         if (dbg && dbg->d_scalar_thr)
             CU(c, cudaMemcpyAsync(dbg->d_scalar_thr, c->scalar_thr, sizeof(int32_t) * n_frames, cudaMemcpyDeviceToDevice, st));
     }
-    CU(c, launch_frontend_tile(fp, st)); c->launches++;
+    {
+        ProfScope ps(c, YSMR_PROF_FRONTEND, st);
+        CU(c, launch_frontend_tile(fp, st)); c->launches++;
+    }
     const int64_t rows = (int64_t)n_frames * c->h;
     if (dbg && dbg->d_mask) { CU(c, launch_unpack_bits(c->mask_bits, dbg->d_mask, rows, c->w, c->ww, st)); c->launches++; }
     if (dbg && dbg->d_markers && fp.marker_bits) { CU(c, launch_unpack_bits(c->marker_bits, dbg->d_markers, rows, c->w, c->ww, st)); c->launches++; }
@@ -341,7 +371,10 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
     L.blob_count = d_blob_count; L.first_xy = c->first_xy; L.counts = c->counts;
     L.work = c->work; L.work_count = &c->ctl->work_count;
     L.status = &c->ctl->status; L.first_bad = &c->ctl->first_bad;
-    CU(c, launch_label(L, std::min(c->label_grid, n_frames), st)); c->launches++;
+    {
+        ProfScope ps(c, YSMR_PROF_LABEL, st);
+        CU(c, launch_label(L, std::min(c->label_grid, n_frames), st)); c->launches++;
+    }
     GeoLaunch G{};
     G.h = c->h; G.w = c->w; G.ww = c->ww; G.max_blobs = c->p.max_blobs; G.first_frame = first_frame;
     G.img_bits = img; G.first_xy = c->first_xy; G.work = c->work; G.work_count = &c->ctl->work_count;
@@ -349,7 +382,10 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
     G.big_items = c->big_items; G.big_count = &c->ctl->big_count; G.big_cap = c->big_cap;
     G.pool = c->pool; G.pool_bytes = c->pool_bytes; G.pool_used = &c->ctl->pool_used;
     G.status = &c->ctl->status; G.first_bad = &c->ctl->first_bad;
-    CU(c, launch_geometry(G, st)); c->launches += 2;
+    {
+        ProfScope ps(c, YSMR_PROF_GEOMETRY, st);
+        CU(c, launch_geometry(G, st)); c->launches += 2;
+    }
     if (dbg && dbg->d_out) { CU(c, launch_unpack_bits(img, dbg->d_out, rows, c->w, c->ww, st)); c->launches++; }
     return YSMR_OK;
 }
@@ -368,6 +404,7 @@ static int link_impl(ysmr_ctx *c, const int32_t *d_blob_count, const float *d_bl
     io.blob_count = d_blob_count; io.blobs = d_blobs; io.rows = (RowOut *)d_rows; io.rows_capacity = rows_capacity;
     io.n_rows = (long long *)d_n_rows; io.append = append;
     io.status = &c->ctl->status; io.first_bad = &c->ctl->first_bad;
+    ProfScope ps(c, YSMR_PROF_LINK, st);
     CU(c, launch_link(c->lc, c->ls, c->lx, io, first_frame, n_frames, st)); c->launches++;
     return YSMR_OK;
 }
@@ -551,5 +588,31 @@ int ysmr_track_host(ysmr_ctx *c, const uint8_t *h_frames, int n_frames, int64_t 
 }
 
 int64_t ysmr_launch_count(const ysmr_ctx *c) { return c ? c->launches : 0; }
+
+int ysmr_set_profiling(ysmr_ctx *c, int enabled)
+{
+    if (!c) return YSMR_E_INVALID;
+    c->profiling = enabled ? 1 : 0;
+    return YSMR_OK;
+}
+
+int ysmr_get_profile(ysmr_ctx *c, double *ms, int64_t *launches)
+{
+    if (!c || !ms || !launches) return fail(c, YSMR_E_INVALID, "null argument");
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    for (int k = 0; k < YSMR_PROF_KINDS; ++k) {
+        double total = 0.0;
+        for (auto &pr : c->prof_events[k]) {
+            float t = 0.f;
+            CU(c, cudaEventElapsedTime(&t, pr.first, pr.second));
+            total += t;
+            c->prof_free.push_back(pr.first); c->prof_free.push_back(pr.second);
+        }
+        ms[k] = total; launches[k] = (int64_t)c->prof_events[k].size();
+        c->prof_events[k].clear();
+    }
+    return YSMR_OK;
+}
 
 }  // extern "C"

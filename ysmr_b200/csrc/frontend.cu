@@ -18,10 +18,11 @@ namespace ysmr {
 
 __device__ __forceinline__ int reflect101(int p, int n)
 {
-    // valid for -n < p < 2n-1, which holds for halos of at most 6 with n >= 16
+    // one reflection is exact for -n < p < 2n-1 (all positions whose value is ever used: halos of at most 6 with
+    // n >= 16); positions further out only occur in tiles hanging over the image edge and are clamped to stay in bounds
     if (p < 0) p = -p;
     if (p >= n) p = 2 * n - 2 - p;
-    return p;
+    return p < 0 ? 0 : (p >= n ? n - 1 : p);
 }
 
 __device__ __forceinline__ int clampi(int p, int n) { return p < 0 ? 0 : (p >= n ? n - 1 : p); }
