@@ -30,7 +30,7 @@ def _check(got, rows):
     assert (got['frame'] == rows[:, 0]).all() and (got['track_id'] == rows[:, 1]).all()      # ids bit-exact
     for k, col in (('w', 4), ('h', 5), ('deg', 6)):
         assert (got[k] == rows[:, col].astype(np.float32)).all()
-    age = coasting_age(rows[:, 4:].sum(1) == 0, rows[:, 1].astype(int))
+    age = coasting_age(rows[:, 4:], rows[:, 1].astype(int))
     err = np.maximum(np.abs(got['x'] - rows[:, 2]) / np.maximum(1, np.abs(rows[:, 2])),
                      np.abs(got['y'] - rows[:, 3]) / np.maximum(1, np.abs(rows[:, 3])))
     assert err[age <= 8].max() < 1e-5, err[age <= 8].max()

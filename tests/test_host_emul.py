@@ -147,7 +147,7 @@ def test_link_logic_equals_reference(emul, path, chunk):
     # positions: 1e-5 relative wherever the track saw a detection within the last 8 frames (an unmatched
     # track feeds its own prediction back, which amplifies last-bit differences by ~6x per frame)
     from tests.util import coasting_age
-    age = coasting_age(rows[:, 4:].sum(1) == 0, rows[:, 1].astype(int))
+    age = coasting_age(rows[:, 4:], rows[:, 1].astype(int))
     err = np.maximum(np.abs(got['x'] - rows[:, 2]) / np.maximum(1, np.abs(rows[:, 2])),
                      np.abs(got['y'] - rows[:, 3]) / np.maximum(1, np.abs(rows[:, 3])))
     assert err[age <= 8].max() < 1e-5

@@ -93,15 +93,23 @@ def oracle_rows(frames, settings, fps=30.0, use_gsff=True):
     return np.array(rows, np.float64).reshape(-1, 7), per_frame
 
 
-def coasting_age(rows_wh_zero, track_ids, window=32):
-    """For each row (emission order): the longest run of consecutive unmatched frames (w=h=deg=0) its track had within
-    the last `window` frames.  While a track is unmatched the reference feeds the GSFF prediction back as the next
+def coasting_age(info, track_ids, window=32):
+    """For each row (emission order): the longest run of consecutive UNMATCHED frames its track had within the last
+    `window` frames.  info = (n, 3) array of (w, h, deg).  A track is unmatched in a frame when its info is zeroed
+    (tracker.py:101, 205) or -- in the "more detections than tracks" branch, which neither ages nor zeroes
+    (tracker.py:215-217) -- when it simply repeats the previous frame's info.
+
+    Why tests need this: while a track is unmatched the reference feeds the GSFF prediction back as the next
     measurement (tracker.py:219-227); that loop amplifies last-bit differences (BLAS summation order, exp) by ~6x per
     frame, and the affected measurements stay in the 31-frame filter history after the track is matched again."""
+    info = np.asarray(info)
     age = np.zeros(len(track_ids), np.int32)
-    cur, hist = {}, {}
-    for i, (tid, z) in enumerate(zip(track_ids, rows_wh_zero)):
-        a = cur.get(tid, 0) + 1 if z else 0
+    cur, hist, prev = {}, {}, {}
+    for i, tid in enumerate(track_ids):
+        row = tuple(info[i])
+        unmatched = (row == (0.0, 0.0, 0.0)) or (prev.get(tid) == row)
+        prev[tid] = row
+        a = cur.get(tid, 0) + 1 if unmatched else 0
         cur[tid] = a
         h = hist.setdefault(tid, [])
         h.append(a)

@@ -48,6 +48,7 @@ struct ysmr_ctx {
     int img_is_marker = 0;        // DIRECT on the marker image (dark-on-light quirk)
     int t_mask = 0, t_marker = 0, inverted = 0, signed_offset = 0;
     int window = 0;               // mean/std moving window (frames)
+    int use_tile = 0;             // YSMR_FRONTEND=tile: run the simple tile kernel instead of the strip kernel
     std::string err;
     int64_t launches = 0;
 
@@ -186,6 +187,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     ysmr_ctx *c = new ysmr_ctx();
     c->device = device; c->h = height; c->w = width; c->ww = (width + 31) / 32; c->channels = channels; c->p = *params;
     derive_thresholds(c);
+    { const char *fe = getenv("YSMR_FRONTEND"); c->use_tile = fe && strcmp(fe, "tile") == 0; }
 #define CC(expr)                                                                                                       \
     do {                                                                                                               \
         cudaError_t e__ = (expr);                                                                                      \
@@ -353,9 +355,15 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
         if (dbg && dbg->d_scalar_thr)
             CU(c, cudaMemcpyAsync(dbg->d_scalar_thr, c->scalar_thr, sizeof(int32_t) * n_frames, cudaMemcpyDeviceToDevice, st));
     }
-    {
-        ProfScope ps(c, YSMR_PROF_FRONTEND, st);
+    if (c->use_tile || (dbg && (dbg->d_grey || dbg->d_blurred || dbg->d_mean))) {
+        // tile kernel: the only one that can dump grey / blurred / mean.  Unless forced (YSMR_FRONTEND=tile) its masks are
+        // then overwritten by the production kernel below, so the mask dumps always come from the production path.
+        ProfScope ps(c, c->use_tile ? YSMR_PROF_FRONTEND : YSMR_PROF_GEOMETRY, st);
         CU(c, launch_frontend_tile(fp, st)); c->launches++;
+    }
+    if (!c->use_tile) {
+        ProfScope ps(c, YSMR_PROF_FRONTEND, st);
+        CU(c, launch_frontend_strip(fp, st)); c->launches++;
     }
     const int64_t rows = (int64_t)n_frames * c->h;
     if (dbg && dbg->d_mask) { CU(c, launch_unpack_bits(c->mask_bits, dbg->d_mask, rows, c->w, c->ww, st)); c->launches++; }

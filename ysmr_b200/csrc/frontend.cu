@@ -124,6 +124,319 @@ __global__ void __launch_bounds__(256) frontend_tile_kernel(FrontParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
+// Strip kernel (production)
+//
+// Work item = (frame, 128-column strip, row chunk), one per WARP; warps never synchronise with each other.
+// Lane l owns the 4 adjacent columns x0 = xs + 4l.  The warp walks down the rows; step s handles blurred row
+// br = y0 - 5 + s (clamped: BORDER_REPLICATE of the Gaussian):
+//   grey rows br-1, br, br+1 (REFLECT_101) live in three packed registers (u8x4) that slide down;
+//   vertical 1-2-1 sums in packed 16-bit lanes, horizontal neighbours by shuffle, blurred -> float -> shared row buffer;
+//   row pass of the 11-tap Gaussian from 5 x LDS.128 (OpenCV's FMA order), result into an 11-row register window;
+//   column pass for output row y0 + s - 10 from that window, rint via the 1.5*2^23 trick, two integer compares against
+//   the blurred value queued 5 steps ago, nibbles OR-reduced over 8 lanes into mask words.
+// Steps are unrolled by 11 (= window depth) so that every window index is a compile-time constant.  The 2 x 5 halo
+// columns the strip needs from its neighbours are produced once per 11 steps by 22 otherwise idle lanes ("halo pass").
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr int STRIP_W = 128;
+constexpr int STRIP_WARPS = 4;
+constexpr int ROWBUF_W = STRIP_W + 16;            // 8 halo floats each side (5 used), keeps LDS.128 aligned
+constexpr float KG0 = 0.00881223008f, KG1 = 0.0271435864f, KG2 = 0.0651140586f, KG3 = 0.121649072f, KG4 = 0.176998362f,
+                KG5 = 0.200565413f;
+
+template <int C>
+__device__ __forceinline__ uint32_t grey_px(const uint8_t *frame, int w, int y, int x)
+{
+    const uint8_t *p = frame + ((int64_t)y * w + x) * C;
+    if (C == 3) return luma(p[0], p[1], p[2]);
+    return p[0];
+}
+
+// 4 grey pixels x0..x0+3 of row y packed little-endian (pixel x0 in bits 0-7).  fast: all four inside the image and the
+// address 4-byte aligned; otherwise per-pixel loads with REFLECT_101 (+ clamp for lanes hanging over the right edge).
+template <int C>
+__device__ __forceinline__ uint32_t load_grey4(const uint8_t *frame, int w, int y, int x0, bool fast)
+{
+    if (fast) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(frame + ((int64_t)y * w + x0) * C);
+        if (C == 1) return __ldg(q);
+        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
+        const uint32_t g0 = luma(w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF);
+        const uint32_t g1 = luma(w0 >> 24, w1 & 0xFF, (w1 >> 8) & 0xFF);
+        const uint32_t g2 = luma((w1 >> 16) & 0xFF, w1 >> 24, w2 & 0xFF);
+        const uint32_t g3 = luma((w2 >> 8) & 0xFF, (w2 >> 16) & 0xFF, w2 >> 24);
+        return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+    }
+    uint32_t r = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) r |= grey_px<C>(frame, w, y, reflect101(x0 + k, w)) << (8 * k);
+    return r;
+}
+
+__device__ __forceinline__ float u8_to_float(uint32_t packed16, int half)
+{
+    // exact int -> float without the conversion pipe: 0x4B000000 | v is 8388608 + v
+    const uint32_t bits = __byte_perm(packed16, 0x4B000000u, half ? 0x7442 : 0x7440);
+    return __uint_as_float(bits) - 8388608.0f;
+}
+
+template <bool TAIL>
+__device__ __forceinline__ float gauss_row(const float *a, bool tail)
+{
+    // a[0..10] = blurred[x-5 .. x+5]
+    float acc = __fmul_rn(KG0, a[0]);
+    if (TAIL && tail) {
+        acc = __fadd_rn(acc, __fmul_rn(KG1, a[1])); acc = __fadd_rn(acc, __fmul_rn(KG2, a[2]));
+        acc = __fadd_rn(acc, __fmul_rn(KG3, a[3])); acc = __fadd_rn(acc, __fmul_rn(KG4, a[4]));
+        acc = __fadd_rn(acc, __fmul_rn(KG5, a[5])); acc = __fadd_rn(acc, __fmul_rn(KG4, a[6]));
+        acc = __fadd_rn(acc, __fmul_rn(KG3, a[7])); acc = __fadd_rn(acc, __fmul_rn(KG2, a[8]));
+        acc = __fmaf_rn(KG1, a[9], acc); acc = __fmaf_rn(KG0, a[10], acc);
+        return acc;
+    }
+    acc = __fmaf_rn(KG1, a[1], acc); acc = __fmaf_rn(KG2, a[2], acc); acc = __fmaf_rn(KG3, a[3], acc);
+    acc = __fmaf_rn(KG4, a[4], acc); acc = __fmaf_rn(KG5, a[5], acc); acc = __fmaf_rn(KG4, a[6], acc);
+    acc = __fmaf_rn(KG3, a[7], acc); acc = __fmaf_rn(KG2, a[8], acc); acc = __fmaf_rn(KG1, a[9], acc);
+    acc = __fmaf_rn(KG0, a[10], acc);
+    return acc;
+}
+
+template <bool TAIL>
+__device__ __forceinline__ float gauss_col(float c, float m1, float p1, float m2, float p2, float m3, float p3, float m4,
+                                           float p4, float m5, float p5, bool tail)
+{
+    float acc = __fmul_rn(KG5, c);
+    const float s1 = __fadd_rn(m1, p1), s2 = __fadd_rn(m2, p2), s3 = __fadd_rn(m3, p3), s4 = __fadd_rn(m4, p4),
+                s5 = __fadd_rn(m5, p5);
+    if (TAIL && tail) {
+        acc = __fadd_rn(acc, __fmul_rn(KG4, s1)); acc = __fadd_rn(acc, __fmul_rn(KG3, s2));
+        acc = __fadd_rn(acc, __fmul_rn(KG2, s3)); acc = __fadd_rn(acc, __fmul_rn(KG1, s4));
+        acc = __fadd_rn(acc, __fmul_rn(KG0, s5));
+        return acc;
+    }
+    acc = __fmaf_rn(KG4, s1, acc); acc = __fmaf_rn(KG3, s2, acc); acc = __fmaf_rn(KG2, s3, acc);
+    acc = __fmaf_rn(KG1, s4, acc); acc = __fmaf_rn(KG0, s5, acc);
+    return acc;
+}
+
+struct StripTask {
+    int frame, strip, y0, y1;
+};
+
+// One step of the register window: store this step's row-pass results / blurred pixels in slot J and run the column
+// pass centred 5 steps back.  J is a template parameter so that every window index is a compile-time constant; the
+// caller dispatches on (step % 11) with a switch, which keeps the rest of the step loop un-unrolled (a fully unrolled
+// body would be ~45 KB of code and thrash the instruction cache).
+template <int J, bool TAIL>
+__device__ __forceinline__ void window_step(float (&win)[11][4], uint32_t (&bq)[11], const float (&r)[4], uint32_t bcur,
+                                            bool col_tail, float (&m)[4], uint32_t &bc)
+{
+    constexpr int c = (J + 6) % 11;            // (J - 5) mod 11
+#pragma unroll
+    for (int k = 0; k < 4; ++k) win[J][k] = r[k];
+    bq[J] = bcur;                              // blurred px0..px3 as bytes
+    bc = bq[c];
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+        m[k] = gauss_col<TAIL>(win[c][k], win[(c + 10) % 11][k], win[(c + 1) % 11][k], win[(c + 9) % 11][k], win[(c + 2) % 11][k],
+                               win[(c + 8) % 11][k], win[(c + 3) % 11][k], win[(c + 7) % 11][k], win[(c + 4) % 11][k],
+                               win[(c + 6) % 11][k], win[(c + 5) % 11][k], col_tail);
+}
+
+// Halo pass for one (step, side): blurred at the 5 columns next to the strip (clamped = BORDER_REPLICATE of the Gaussian;
+// neighbours with REFLECT_101 = border of the 3x3 blur) and the vertical sum of the adjacent column.
+template <int C>
+__device__ __forceinline__ void halo_side(const uint8_t *frame, int w, int h, int br, int xs, int side, float *dst, uint32_t *vh_out)
+{
+    const int ym = reflect101(br - 1, h), yp = reflect101(br + 1, h);
+    const int xb = side ? xs + STRIP_W : xs - 5;          // first of the 5 blurred columns
+    auto vsum = [&](int x) -> int {
+        return (int)grey_px<C>(frame, w, ym, x) + 2 * (int)grey_px<C>(frame, w, br, x) + (int)grey_px<C>(frame, w, yp, x);
+    };
+    if (xb - 1 >= 0 && xb + 5 < w) {
+        int v[7];
+#pragma unroll
+        for (int k = 0; k < 7; ++k) v[k] = vsum(xb - 1 + k);
+#pragma unroll
+        for (int k = 0; k < 5; ++k) dst[k] = (float)((v[k] + 2 * v[k + 1] + v[k + 2] + 8) >> 4);
+        *vh_out = (uint32_t)(side ? v[1] : v[5]);          // column xs+128 resp. xs-1
+    } else {
+        for (int k = 0; k < 5; ++k) {
+            const int cx = clampi(xb + k, w);
+            dst[k] = (float)((vsum(reflect101(cx - 1, w)) + 2 * vsum(cx) + vsum(reflect101(cx + 1, w)) + 8) >> 4);
+        }
+        *vh_out = (uint32_t)vsum(reflect101(side ? xs + STRIP_W : xs - 1, w));
+    }
+}
+
+template <int C, bool EDGE>
+__device__ __forceinline__ void strip_run(const FrontParams &p, const StripTask t, float (*rowbuf)[ROWBUF_W], uint32_t (*vh)[2])
+{
+    const int lane = threadIdx.x & 31;
+    const int xs = t.strip * STRIP_W;
+    const int x0 = xs + 4 * lane;
+    const uint8_t *frame = p.frames + (int64_t)t.frame * p.frame_stride;
+    const int w = p.w, h = p.h;
+    // fast loads: the lane's 4 pixels are inside the image and 4-byte aligned in every row
+    const bool aligned = ((reinterpret_cast<uintptr_t>(frame) & 3) == 0) && (((int64_t)w * C) % 4 == 0);
+    const bool fast = aligned && (x0 + 3 < w);
+    const bool row_tail = EDGE && (x0 >= p.row_tail_from);
+    const bool col_tail = EDGE && (x0 >= p.col_tail_from);
+    uint32_t valid_nib = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) valid_nib |= (x0 + k < w) ? (1u << k) : 0u;
+    const uint32_t inv_nib = p.inverted ? 0xFu : 0u;
+    const int shift = 4 * (lane & 7);
+    const int word = (xs >> 5) + (lane >> 3);
+    const bool scalar_mode = p.scalar_thr != nullptr;
+    // Packed compare (two pixels per 32-bit add, 16-bit lanes): X = B + K - M with B = blurred pair, M = mean pair and
+    // K = 0x8000 - t - 1 per lane; bit 15 of a lane is set iff b - mean - t - 1 >= 0, i.e. d > t.  In the mean/std mode the
+    // mean is replaced by 0 and t by the frame's scalar threshold (cv2.threshold: src > T).
+    auto lim = [](int v) { return v < -30000 ? -30000 : (v > 30000 ? 30000 : v); };   // keeps the 16-bit lanes apart
+    const int t_a = lim(scalar_mode ? p.scalar_thr[t.frame] : p.t_mask);
+    const int t_b = lim(scalar_mode ? 30000 : p.t_marker);       // marker image unused in the mean/std mode
+    const uint32_t k_a = (uint32_t)((0x8000 - t_a - 1) & 0xFFFF) * 0x00010001u;
+    const uint32_t k_b = (uint32_t)((0x8000 - t_b - 1) & 0xFFFF) * 0x00010001u;
+    const uint32_t mean_keep = scalar_mode ? 0u : 0xFFFFFFFFu;
+    // REPLICATE source for pixels right of the image (EDGE strips only)
+    const int e_owner = (w - 1 - xs) >> 2, e_pos = (w - 1 - xs) & 3;
+
+    float win[11][4];                 // row-pass results of the last 11 steps
+    uint32_t bq[11];                  // blurred (u8x4) of the last 11 steps
+#pragma unroll
+    for (int i = 0; i < 11; ++i) { bq[i] = 0; win[i][0] = win[i][1] = win[i][2] = win[i][3] = 0.f; }
+
+    const int n_steps = (t.y1 - t.y0) + 10;
+    int cbr = clampi(t.y0 - 5, h);    // clamped blurred row of the current step
+    uint32_t gp = load_grey4<C>(frame, w, reflect101(cbr - 1, h), x0, fast);   // grey rows br-1, br, br+1
+    uint32_t gc = load_grey4<C>(frame, w, cbr, x0, fast);
+    uint32_t gn = load_grey4<C>(frame, w, reflect101(cbr + 1, h), x0, fast);
+    uint32_t pre = 0;
+    uint32_t *out_mask = p.mask_bits + ((int64_t)t.frame * h) * p.ww + word;
+    uint32_t *out_mark = p.marker_bits ? p.marker_bits + ((int64_t)t.frame * h) * p.ww + word : nullptr;
+    const bool writer = (lane & 7) == 0 && word < p.ww;
+
+    int j = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        if (j == 0) {
+            // halo pass for steps s .. s+10: lanes 0..21 = (step, side)
+            __syncwarp();
+            if (lane < 22) {
+                const int jj = lane >> 1, side = lane & 1;
+                halo_side<C>(frame, w, h, clampi(t.y0 - 5 + s + jj, h), xs, side, &rowbuf[jj][side ? 8 + STRIP_W : 3], &vh[jj][side]);
+            }
+            __syncwarp();
+        }
+        // prefetch the grey row the NEXT step will need (if it advances)
+        const int next_cbr = clampi(t.y0 - 5 + s + 1, h);
+        const bool adv_next = next_cbr != cbr;
+        if (adv_next) pre = load_grey4<C>(frame, w, reflect101(next_cbr + 1, h), x0, fast);
+
+        // vertical 1-2-1 sums, packed 16-bit: lo = (px0, px1), hi = (px2, px3)
+        const uint32_t v_lo = __byte_perm(gp, 0, 0x4140) + 2 * __byte_perm(gc, 0, 0x4140) + __byte_perm(gn, 0, 0x4140);
+        const uint32_t v_hi = __byte_perm(gp, 0, 0x4342) + 2 * __byte_perm(gc, 0, 0x4342) + __byte_perm(gn, 0, 0x4342);
+        uint32_t left = __shfl_up_sync(0xffffffffu, v_hi, 1) >> 16;
+        uint32_t right = __shfl_down_sync(0xffffffffu, v_lo, 1) & 0xFFFFu;
+        const uint2 vhj = *reinterpret_cast<const uint2 *>(vh[j]);       // broadcast load, then select: no branches
+        left = lane == 0 ? vhj.x : left;
+        right = lane == 31 ? vhj.y : right;
+        // (REFLECT_101 at the right image edge needs no special case: lanes that hang over the edge load their pixels with
+        //  reflected indices, so the sums of column w and beyond already are those of w-2, ...)
+        const uint32_t vm1_lo = (v_lo << 16) | left;                       // (v[-1], v0)
+        const uint32_t mid = __funnelshift_r(v_lo, v_hi, 16);              // (v1, v2)
+        const uint32_t vp1_hi = (v_hi >> 16) | (right << 16);              // (v3, v[4])
+        uint32_t b_lo = ((vm1_lo + 2 * v_lo + mid + 0x00080008u) >> 4) & 0x00FF00FFu;   // blurred px0, px1
+        uint32_t b_hi = ((mid + 2 * v_hi + vp1_hi + 0x00080008u) >> 4) & 0x00FF00FFu;   // blurred px2, px3
+        if (EDGE) {
+            // BORDER_REPLICATE of the blurred image for pixels right of the image: value of column w-1
+            const uint32_t src = e_pos < 2 ? b_lo : b_hi;
+            const uint32_t mine = (e_pos & 1) ? (src >> 16) : (src & 0xFFFFu);
+            const uint32_t edge = __shfl_sync(0xffffffffu, mine, e_owner);
+            if (x0 + 0 >= w) b_lo = (b_lo & 0xFFFF0000u) | edge;
+            if (x0 + 1 >= w) b_lo = (b_lo & 0x0000FFFFu) | (edge << 16);
+            if (x0 + 2 >= w) b_hi = (b_hi & 0xFFFF0000u) | edge;
+            if (x0 + 3 >= w) b_hi = (b_hi & 0x0000FFFFu) | (edge << 16);
+        }
+        const uint32_t bcur = __byte_perm(b_lo, b_hi, 0x6420);
+        float4 f;
+        f.x = u8_to_float(b_lo, 0); f.y = u8_to_float(b_lo, 1); f.z = u8_to_float(b_hi, 0); f.w = u8_to_float(b_hi, 1);
+        float *rb = rowbuf[j];
+        *reinterpret_cast<float4 *>(&rb[8 + 4 * lane]) = f;
+        __syncwarp();
+        float a[20];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4 *>(&rb[4 * lane + 4 * q]);
+            a[4 * q] = t4.x; a[4 * q + 1] = t4.y; a[4 * q + 2] = t4.z; a[4 * q + 3] = t4.w;
+        }
+        float r[4], m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = gauss_row<EDGE>(&a[3 + k], row_tail);
+        uint32_t bc;
+        switch (j) {
+            case 0: window_step<0, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 1: window_step<1, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 2: window_step<2, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 3: window_step<3, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 4: window_step<4, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 5: window_step<5, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 6: window_step<6, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 7: window_step<7, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 8: window_step<8, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            case 9: window_step<9, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+            default: window_step<10, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
+        }
+        // ---- compare for output row y = y0 + s - 10 (centre = step s-5)
+        // rint (half to even) by adding 1.5 * 2^23: the low 16 bits of the float's bit pattern are the rounded mean
+        const uint32_t i0 = __float_as_uint(__fadd_rn(m[0], 12582912.0f)), i1 = __float_as_uint(__fadd_rn(m[1], 12582912.0f));
+        const uint32_t i2 = __float_as_uint(__fadd_rn(m[2], 12582912.0f)), i3 = __float_as_uint(__fadd_rn(m[3], 12582912.0f));
+        const uint32_t mean_lo = __byte_perm(i0, i1, 0x5410) & mean_keep;       // (mean0, mean1) as 16-bit lanes
+        const uint32_t mean_hi = __byte_perm(i2, i3, 0x5410) & mean_keep;
+        const uint32_t bl = __byte_perm(bc, 0, 0x4140), bh = __byte_perm(bc, 0, 0x4342);
+        const uint32_t xa_lo = bl + k_a - mean_lo, xa_hi = bh + k_a - mean_hi;
+        const uint32_t xb_lo = bl + k_b - mean_lo, xb_hi = bh + k_b - mean_hi;
+        // gather bits 15 / 31 of the two registers into a nibble: bytes 1 and 3 -> flags in bit 7 of four bytes -> multiply
+        auto nibble = [](uint32_t lo, uint32_t hi) -> uint32_t {
+            const uint32_t y = (__byte_perm(lo, hi, 0x7531) >> 7) & 0x01010101u;
+            return (y * 0x01020408u) >> 24;
+        };
+        uint32_t nib_mask = (nibble(xa_lo, xa_hi) ^ inv_nib) & valid_nib;
+        uint32_t nib_mark = (nibble(xb_lo, xb_hi) ^ inv_nib) & valid_nib;
+        uint32_t wm = nib_mask << shift, wk = nib_mark << shift;
+        wm |= __shfl_xor_sync(0xffffffffu, wm, 1); wk |= __shfl_xor_sync(0xffffffffu, wk, 1);
+        wm |= __shfl_xor_sync(0xffffffffu, wm, 2); wk |= __shfl_xor_sync(0xffffffffu, wk, 2);
+        wm |= __shfl_xor_sync(0xffffffffu, wm, 4); wk |= __shfl_xor_sync(0xffffffffu, wk, 4);
+        if (s >= 10 && writer) {
+            const int64_t o = (int64_t)(t.y0 + s - 10) * p.ww;
+            out_mask[o] = wm;
+            if (out_mark) out_mark[o] = wk;
+        }
+        // slide the grey window
+        if (adv_next) { gp = gc; gc = gn; gn = pre; cbr = next_cbr; }
+        j = j == 10 ? 0 : j + 1;
+    }
+}
+
+template <int C>
+__global__ void __launch_bounds__(STRIP_WARPS * 32, 4) frontend_strip_kernel(FrontParams p, int n_strips, int n_chunks, int rows_per_chunk)
+{
+    __shared__ __align__(16) float rowbuf[STRIP_WARPS][11][ROWBUF_W];
+    __shared__ uint32_t vh[STRIP_WARPS][11][2];
+    const int warp = threadIdx.x >> 5;
+    const int64_t task = (int64_t)blockIdx.x * STRIP_WARPS + warp;
+    const int64_t per_frame = (int64_t)n_strips * n_chunks;
+    if (task >= per_frame * p.n_frames) return;
+    StripTask t;
+    t.frame = (int)(task / per_frame);
+    const int r = (int)(task - (int64_t)t.frame * per_frame);
+    t.strip = r % n_strips;                   // neighbouring warps take neighbouring strips of the same rows (L1/L2 reuse)
+    const int chunk = r / n_strips;
+    t.y0 = chunk * rows_per_chunk;
+    t.y1 = min(p.h, t.y0 + rows_per_chunk);
+    const bool edge = (t.strip == n_strips - 1);       // the only strip that can hang over the right image edge
+    if (edge) strip_run<C, true>(p, t, rowbuf[warp], vh[warp]);
+    else strip_run<C, false>(p, t, rowbuf[warp], vh[warp]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
 // Small helpers used by the debug path and the mean/std mode
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void unpack_bits_kernel(const uint32_t *bits, uint8_t *bytes, int64_t rows, int w, int ww)
@@ -215,6 +528,19 @@ cudaError_t launch_frontend_tile(const FrontParams &p, cudaStream_t st)
     dim3 grid((p.w + TILE_W - 1) / TILE_W, (p.h + TILE_H - 1) / TILE_H, p.n_frames);
     if (p.channels == 3) frontend_tile_kernel<3><<<grid, 256, 0, st>>>(p);
     else frontend_tile_kernel<1><<<grid, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frontend_strip(const FrontParams &p, cudaStream_t st)
+{
+    const int n_strips = (p.w + STRIP_W - 1) / STRIP_W;
+    int n_chunks = (p.h + 115) / 230;
+    if (n_chunks < 1) n_chunks = 1;
+    const int rows_per_chunk = (p.h + n_chunks - 1) / n_chunks;
+    const int64_t tasks = (int64_t)n_strips * n_chunks * p.n_frames;
+    const unsigned grid = (unsigned)((tasks + STRIP_WARPS - 1) / STRIP_WARPS);
+    if (p.channels == 3) frontend_strip_kernel<3><<<grid, STRIP_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
+    else frontend_strip_kernel<1><<<grid, STRIP_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
     return cudaGetLastError();
 }
 
