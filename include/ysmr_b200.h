@@ -161,6 +161,9 @@ int64_t ysmr_launch_count(const ysmr_ctx *ctx);
 enum { YSMR_PROF_FRONTEND = 0, YSMR_PROF_LABEL = 1, YSMR_PROF_GEOMETRY = 2, YSMR_PROF_LINK = 3, YSMR_PROF_KINDS = 4 };
 int ysmr_set_profiling(ysmr_ctx *ctx, int enabled);
 int ysmr_get_profile(ysmr_ctx *ctx, double *ms, int64_t *launches);
+/* With ysmr_set_profiling(ctx, 3) the linker's shared-memory path also accumulates SM cycles per phase (clock64 of
+ * thread 0): out16[0..8] = the nine barrier-delimited phases of a frame, out16[12] = frames.  Clears the counters. */
+int ysmr_link_phase_cycles(ysmr_ctx *ctx, int64_t *out16);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,24 @@
+import numpy as np, torch, sys
+sys.path.insert(0,'.')
+from ysmr_b200.api import Context
+from ysmr_b200.synth import SceneConfig, make_scene, render_frames_torch
+F=1024
+scene=make_scene(SceneConfig(n_frames=F,n_cells=50,seed=0))
+fr=torch.empty((F,922,1228),dtype=torch.uint8,device='cuda')
+for a in range(0,F,128): render_frames_torch(scene,a,a+128,'cuda',1,out=fr[a:a+128])
+ctx=Context(922,1228,1,0,max_batch=256,max_blobs=512,max_tracks=1024)
+cs=[];bs=[]
+for a in range(0,F,256):
+    c,b=ctx.detect(fr[a:a+256],a); cs.append(c); bs.append(b)
+counts=torch.cat(cs); blobs=torch.cat(bs)
+for rep in range(2):
+    ctx.reset(); ctx.set_profiling(True, link_phases=True)
+    torch.cuda.synchronize()
+    e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
+    e0.record(); rows=ctx.link(counts,blobs,0,F*100); e1.record(); torch.cuda.synchronize()
+    pc=ctx.link_phase_cycles()
+    print('link ms', e0.elapsed_time(e1), 'rows', len(rows), 'frames', pc[12])
+    names=['dets+sync1','row minima','col winners','outcome+vote','predsum+row','mode+exp','total+div','out+push','estimate','-']
+    tot=sum(pc[:12])
+    for i in range(9): print('  %-20s %8.0f cyc/frame'%(names[i], pc[i]/max(pc[12],1)))
+    print('  total cyc/frame', tot/max(pc[12],1))

@@ -134,7 +134,8 @@ struct HostLinker {
     LinkScratch x;
     std::vector<std::vector<double>> gains;
     std::vector<int32_t> hdr, order0, order1, free_slots, id, gone, mode, hist_n, hist_pos, col_row, row_arg, list, table;
-    std::vector<double> px, py, hist, wgt, xh, row_min;
+    std::vector<double> px, py, hist, wgt, xh, row_min, mom;
+    std::vector<int32_t> mom_ok;
     std::vector<float> iw, ih, ideg;
     std::vector<unsigned long long> col_best;
     std::vector<uint32_t> flag;
@@ -180,6 +181,8 @@ void *emul_link_create(double fps, int use_gsff, int n_f, const int32_t *n_i, co
     s.id = L->id.data(); s.px = L->px.data(); s.py = L->py.data(); s.iw = L->iw.data(); s.ih = L->ih.data(); s.ideg = L->ideg.data();
     s.gone = L->gone.data(); s.mode = L->mode.data(); s.hist_n = L->hist_n.data(); s.hist_pos = L->hist_pos.data();
     s.hist = L->hist.data(); s.wgt = L->wgt.data(); s.xh = L->xh.data();
+    L->mom.resize((size_t)T * LINK_MAX_FILTERS * 4); L->mom_ok.assign(T, 0);
+    s.mom = L->mom.data(); s.mom_ok = L->mom_ok.data();
     L->col_best.resize(B); L->col_row.resize(B); L->row_min.resize(T); L->row_arg.resize(T);
     L->flag.resize((T > B ? T : B) + 2); L->list.resize(B); L->table.resize(set_table_capacity(B));
     LinkScratch &x = L->x;

@@ -69,6 +69,7 @@ EXPORTS = {
     'ysmr_launch_count': (C.c_int64, [C.c_void_p]),
     'ysmr_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
     'ysmr_get_profile': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
+    'ysmr_link_phase_cycles': (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
 }
 
 _lib = None

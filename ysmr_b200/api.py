@@ -211,8 +211,13 @@ class Context:
 
     PROF_KINDS = ('frontend', 'label', 'geometry', 'link')
 
-    def set_profiling(self, enabled=True):
-        self._check(self.lib.ysmr_set_profiling(self._h, int(bool(enabled))))
+    def set_profiling(self, enabled=True, link_phases=False):
+        self._check(self.lib.ysmr_set_profiling(self._h, (1 if enabled else 0) | (2 if link_phases else 0)))
+
+    def link_phase_cycles(self):
+        out = (C.c_int64 * 16)()
+        self._check(self.lib.ysmr_link_phase_cycles(self._h, out))
+        return list(out)
 
     def get_profile(self):
         """{kind: (total_ms, launches)} since the last call; synchronises the device."""

@@ -48,6 +48,8 @@ struct ysmr_ctx {
     int img_is_marker = 0;        // DIRECT on the marker image (dark-on-light quirk)
     int t_mask = 0, t_marker = 0, inverted = 0, signed_offset = 0;
     int window = 0;               // mean/std moving window (frames)
+    int gains_affine = 1;         // all uploaded FIR gains are affine in the tap index (required by the fast linker)
+    int link_fast = 1;            // YSMR_LINK=general disables the shared-memory fast path of the linker (tests)
     int use_tile = 0;             // YSMR_FRONTEND=tile: run the simple tile kernel instead of the strip kernel
     std::string err;
     int64_t launches = 0;
@@ -64,6 +66,7 @@ struct ysmr_ctx {
     LinkConfig lc{};
     LinkState ls{};
     LinkScratch lx{};
+    long long *phase_cycles = nullptr;
     double *gain_dev[LINK_MAX_FILTERS] = {nullptr, nullptr, nullptr, nullptr};
     bool gain_set[LINK_MAX_FILTERS] = {false, false, false, false};
     std::vector<std::pair<void *, size_t>> state_parts;   // for export/import
@@ -188,6 +191,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     c->device = device; c->h = height; c->w = width; c->ww = (width + 31) / 32; c->channels = channels; c->p = *params;
     derive_thresholds(c);
     { const char *fe = getenv("YSMR_FRONTEND"); c->use_tile = fe && strcmp(fe, "tile") == 0; }
+    { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strcmp(lk, "general") == 0); }
 #define CC(expr)                                                                                                       \
     do {                                                                                                               \
         cudaError_t e__ = (expr);                                                                                      \
@@ -254,6 +258,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     CC(part(&ls.gone, T)); CC(part(&ls.mode, T)); CC(part(&ls.hist_n, T)); CC(part(&ls.hist_pos, T));
     CC(part(&ls.hist, T * (size_t)lc.hist_len * 2));
     CC(part(&ls.wgt, T * LINK_MAX_FILTERS)); CC(part(&ls.xh, T * LINK_MAX_FILTERS * 2));
+    CC(part(&ls.mom, T * LINK_MAX_FILTERS * 4)); CC(part(&ls.mom_ok, T));
     for (auto &pr : c->state_parts) CC(cudaMemset(pr.first, 0, pr.second));
     LinkScratch &lx = c->lx;
     CC(dev_alloc(c, &lx.col_best, MB)); CC(dev_alloc(c, &lx.col_row, MB));
@@ -261,6 +266,9 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     CC(dev_alloc(c, &lx.flag, std::max(T, MB) + 2)); CC(dev_alloc(c, &lx.list, MB));
     lx.set_table_size = set_table_capacity((int)MB);
     CC(dev_alloc(c, &lx.table, (size_t)lx.set_table_size));
+    CC(dev_alloc(c, &c->phase_cycles, 16));
+    CC(cudaMemset(c->phase_cycles, 0, 16 * sizeof(long long)));
+    lx.phase_cycles = nullptr;
     for (int i = 0; i < lc.n_f; ++i) CC(dev_alloc(c, &c->gain_dev[i], (size_t)4 * lc.n_i[i]));
     for (int i = 0; i < LINK_MAX_FILTERS; ++i) lc.gain[i] = c->gain_dev[i];
     CC(launch_link_reset(ls, params->max_tracks, nullptr)); c->launches++;
@@ -321,6 +329,14 @@ int ysmr_set_gsff_gain(ysmr_ctx *c, int filter, int horizon, const double *h_gai
         g[k] = h_gain[2 * k]; g[n + k] = h_gain[2 * k + 1];
         g[2 * n + k] = h_gain[2 * n + 2 * k]; g[3 * n + k] = h_gain[2 * n + 2 * k + 1];
         if (g[n + k] != 0.0 || g[2 * n + k] != 0.0) c->lc.cross_zero = 0;
+    }
+    // The linker's fast path evaluates the filter as alpha*S0 + beta*S1 (link.cu), which needs gains affine in the tap
+    // index.  The reference's gains are (one-step-ahead line fit); anything else falls back to the general path.
+    for (int arr = 0; arr < 4; arr += 3) {
+        const double *a = g.data() + (size_t)arr * n;
+        const double beta = n > 1 ? (a[n - 1] - a[0]) / (double)(n - 1) : 0.0;
+        for (int k = 0; k < n; ++k)
+            if (fabs(a[k] - (a[0] + beta * k)) > 1e-13 * (1.0 + fabs(a[k]))) c->gains_affine = 0;
     }
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaMemcpy(c->gain_dev[filter], g.data(), sizeof(double) * g.size(), cudaMemcpyHostToDevice));
@@ -413,7 +429,7 @@ static int link_impl(ysmr_ctx *c, const int32_t *d_blob_count, const float *d_bl
     io.n_rows = (long long *)d_n_rows; io.append = append;
     io.status = &c->ctl->status; io.first_bad = &c->ctl->first_bad;
     ProfScope ps(c, YSMR_PROF_LINK, st);
-    CU(c, launch_link(c->lc, c->ls, c->lx, io, first_frame, n_frames, st)); c->launches++;
+    CU(c, launch_link(c->lc, c->ls, c->lx, io, first_frame, n_frames, c->link_fast && c->gains_affine, st)); c->launches++;
     return YSMR_OK;
 }
 
@@ -601,6 +617,17 @@ int ysmr_set_profiling(ysmr_ctx *c, int enabled)
 {
     if (!c) return YSMR_E_INVALID;
     c->profiling = enabled ? 1 : 0;
+    c->lx.phase_cycles = (enabled & 2) ? c->phase_cycles : nullptr;     // bit 1: per-phase clock64 counters in the linker
+    return YSMR_OK;
+}
+
+int ysmr_link_phase_cycles(ysmr_ctx *c, int64_t *out16)
+{
+    if (!c || !out16) return YSMR_E_INVALID;
+    CU(c, cudaSetDevice(c->device));
+    CU(c, cudaDeviceSynchronize());
+    CU(c, cudaMemcpy(out16, c->phase_cycles, 16 * sizeof(long long), cudaMemcpyDeviceToHost));
+    CU(c, cudaMemset(c->phase_cycles, 0, 16 * sizeof(long long)));
     return YSMR_OK;
 }
 

@@ -50,6 +50,8 @@ struct LinkState {
     double *hist;                        //   [slot][hist_len][2]
     double *wgt;                         //   [slot][LINK_MAX_FILTERS]
     double *xh;                          //   [slot][LINK_MAX_FILTERS][2]
+    double *mom;                         //   [slot][LINK_MAX_FILTERS][4] window moments S0x,S0y,S1x,S1y (fast path cache)
+    int32_t *mom_ok;                     //   [slot] 1 while `mom` matches the history (only the fast path maintains it)
 };
 
 // Per-frame scratch (device: global memory owned by the context).
@@ -62,6 +64,7 @@ struct LinkScratch {
     int32_t *list;                       // [max_blobs] unused detections ascending, then in registration order
     int32_t *table;                      // [set_table_size] CPython set emulation
     int set_table_size;
+    long long *phase_cycles;             // [16] optional per-phase cycle counters of the fast path (NULL = off)
 };
 
 struct RowOut {                          // must match ysmr_row (include/ysmr_b200.h)
@@ -133,29 +136,11 @@ YSMR_HD void cpython_set_order(int32_t *keys, int n, int32_t *table)
 
 // ---- GSFF (gsff.py) for one track ----------------------------------------------------------------------------------
 
+YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot, int i);
+
 YSMR_HD void gsff_estimates(const LinkConfig &c, const LinkState &s, int slot, int mode)
 {
-    const double *hist = s.hist + (int64_t)slot * c.hist_len * 2;
-    const int pos = s.hist_pos[slot];
-    for (int i = 0; i < mode; ++i) {
-        const int n = c.n_i[i];
-        const double *g = c.gain[i];
-        double ax = 0.0, ay = 0.0;
-        int j = pos - n; if (j < 0) j += c.hist_len;
-        for (int k = 0; k < n; ++k) {
-            const double mx = hist[2 * j], my = hist[2 * j + 1];
-            if (c.cross_zero) {
-                ax = fma(g[k], mx, ax);
-                ay = fma(g[3 * n + k], my, ay);
-            } else {
-                ax = fma(g[k], mx, ax); ax = fma(g[n + k], my, ax);
-                ay = fma(g[2 * n + k], mx, ay); ay = fma(g[3 * n + k], my, ay);
-            }
-            if (++j == c.hist_len) j = 0;
-        }
-        s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2] = ax;
-        s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2 + 1] = ay;
-    }
+    for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i);
 }
 
 YSMR_HD void gsff_push(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy)
@@ -168,9 +153,9 @@ YSMR_HD void gsff_push(const LinkConfig &c, const LinkState &s, int slot, double
     if (s.hist_n[slot] < c.hist_len) s.hist_n[slot] += 1;
 }
 
-// correct() then predict() for one track (tracker.py:221-225).  (zx, zy) = self.objects[key]; out = filtered position
-// written to the CSV; the stored position becomes the prediction.
-YSMR_HD void gsff_step(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy, double *ox, double *oy)
+// GaussianSumFIR.correct (gsff.py:251-347) for one track: (zx, zy) = self.objects[key]; (ox, oy) = the filtered position
+// that goes to the CSV.  Appends z to the history.
+YSMR_HD void gsff_correct(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy, double *ox, double *oy)
 {
     if (s.hist_n[slot] == 0) {                       // first call: previous_measurements = [z] * n_i[0]
         for (int k = 0; k < c.n_i[0]; ++k) gsff_push(c, s, slot, zx, zy);
@@ -208,13 +193,52 @@ YSMR_HD void gsff_step(const LinkConfig &c, const LinkState &s, int slot, double
         else { fx = fx + xh[2 * i] * w[i]; fy = fy + xh[2 * i + 1] * w[i]; }
     }
     *ox = fx; *oy = fy;
-    gsff_estimates(c, s, slot, mode);
+}
+
+// One least-squares FIR estimate (gsff.py:156-177, 230-240) of filter i for the predict step.
+YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot, int i)
+{
+    const double *hist = s.hist + (int64_t)slot * c.hist_len * 2;
+    const int n = c.n_i[i];
+    const double *g = c.gain[i];
+    double ax = 0.0, ay = 0.0;
+    int j = s.hist_pos[slot] - n; if (j < 0) j += c.hist_len;
+    for (int k = 0; k < n; ++k) {
+        const double mx = hist[2 * j], my = hist[2 * j + 1];
+        if (c.cross_zero) {
+            ax = fma(g[k], mx, ax);
+            ay = fma(g[3 * n + k], my, ay);
+        } else {
+            ax = fma(g[k], mx, ax); ax = fma(g[n + k], my, ax);
+            ay = fma(g[2 * n + k], mx, ay); ay = fma(g[3 * n + k], my, ay);
+        }
+        if (++j == c.hist_len) j = 0;
+    }
+    s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2] = ax;
+    s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2 + 1] = ay;
+}
+
+// GaussianSumFIR.predict's weighted sum (gsff.py:242): the stored position becomes the prediction (tracker.py:225).
+YSMR_HD void gsff_combine(const LinkState &s, int slot)
+{
+    const int mode = s.mode[slot];
+    const double *w = s.wgt + (int64_t)slot * LINK_MAX_FILTERS;
+    const double *xh = s.xh + (int64_t)slot * LINK_MAX_FILTERS * 2;
     double qx = 0.0, qy = 0.0;
     for (int i = 0; i < mode; ++i) {
         if (i == 0) { qx = xh[0] * w[0]; qy = xh[1] * w[0]; }
         else { qx = qx + xh[2 * i] * w[i]; qy = qy + xh[2 * i + 1] * w[i]; }
     }
     s.px[slot] = qx; s.py[slot] = qy;
+}
+
+// correct() then predict() for one track (tracker.py:221-225), serial form used by the general path.
+YSMR_HD void gsff_step(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy, double *ox, double *oy)
+{
+    gsff_correct(c, s, slot, zx, zy, ox, oy);
+    const int mode = s.mode[slot];
+    for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i);
+    gsff_combine(s, slot);
 }
 
 // ---- one frame -------------------------------------------------------------------------------------------------------
@@ -238,20 +262,25 @@ YSMR_HD void link_init_track(const LinkConfig &c, const LinkState &s, int slot, 
     s.iw[slot] = det[2]; s.ih[slot] = det[3]; s.ideg[slot] = det[4];
     s.gone[slot] = 0;
     s.mode[slot] = 0; s.hist_n[slot] = 0; s.hist_pos[slot] = 0;
+    s.mom_ok[slot] = 0;
 }
 
 // Processes frames [0, n_frames) of the chunk.  Header values live in registers of every thread and are updated
 // identically by all of them (every quantity they depend on is CTA-uniform), thread 0 writes them back at the end.
 template <class Cta>
 YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const LinkScratch &x, const LinkIo &io,
-                        int first_frame, int n_frames)
+                        int first_frame, int n_frames, int start_frame = 0)
 {
     const int tid = cta.tid(), nthr = cta.nthr();
     int n = s.hdr[0], next_id = s.hdr[1], n_free = s.hdr[2], sel = s.hdr[3];
     long long rows_total = io.append ? *io.n_rows : 0;
     bool row_overflow = false;
+    if (start_frame < n_frames) {          // this path does not maintain the fast path's moment cache
+        for (int r = tid; r < n; r += nthr) s.mom_ok[s.order[sel][r]] = 0;
+        cta.sync();
+    }
 
-    for (int fi = 0; fi < n_frames; ++fi) {
+    for (int fi = start_frame; fi < n_frames; ++fi) {
         const int m = io.blob_count[fi];
         const float *dets = io.blobs + (int64_t)fi * c.max_blobs * 5;
         int32_t *order = s.order[sel];
@@ -376,7 +405,7 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
     }
     if (tid == 0) {
         s.hdr[0] = n; s.hdr[1] = next_id; s.hdr[2] = n_free; s.hdr[3] = sel;
-        s.hdr[4] += n_frames; s.hdr[5] = n;
+        s.hdr[4] += n_frames - start_frame; s.hdr[5] = n;
         *io.n_rows = rows_total;
     }
 }
@@ -404,7 +433,7 @@ YSMR_HD void row_minima_serial(const Cta &cta, const LinkState &s, const int32_t
 
 #if defined(__CUDACC__)
 cudaError_t launch_link(const LinkConfig &c, const LinkState &s, const LinkScratch &x, const LinkIo &io, int first_frame,
-                        int n_frames, cudaStream_t st);
+                        int n_frames, int allow_fast, cudaStream_t st);
 cudaError_t launch_link_reset(const LinkState &s, int max_tracks, cudaStream_t st);
 #endif
 
