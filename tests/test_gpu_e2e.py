@@ -36,8 +36,14 @@ def _check_against_csv(got, ref):
     age = coasting_age(ref[:, 4:], ref[:, 0].astype(int))
     err = np.maximum(np.abs(got['x'] - ref[:, 2]) / np.maximum(1, np.abs(ref[:, 2])),
                      np.abs(got['y'] - ref[:, 3]) / np.maximum(1, np.abs(ref[:, 3])))
-    ok = (age <= 8) & (d.max(1) <= 1e-3)
+    # a tie flip moves that detection's centre by a fraction of a pixel; the measurement then sits in the track's
+    # 31-frame filter history, so the following 31 rows of that track are compared with a pixel-level bound instead
+    tainted = np.zeros(len(ref), bool)
+    for i in np.nonzero(d.max(1) > 1e-3)[0]:
+        tainted |= (ref[:, 0] == ref[i, 0]) & (ref[:, 1] >= ref[i, 1]) & (ref[:, 1] <= ref[i, 1] + 31)
+    ok = (age <= 8) & ~tainted
     assert err[ok].max() < 1e-5, err[ok].max()
+    assert np.abs(got['x'] - ref[:, 2])[tainted].max(initial=0) < 1.0 and np.abs(got['y'] - ref[:, 3])[tainted].max(initial=0) < 1.0
 
 
 @pytest.mark.parametrize('name,channels', [('small_wod', 1), ('small_wod', 3), ('small_dol', 1), ('small_single', 1),

@@ -241,6 +241,29 @@ __device__ __forceinline__ void window_step(float (&win)[11][4], uint32_t (&bq)[
                                win[(c + 6) % 11][k], win[(c + 5) % 11][k], col_tail);
 }
 
+// Image-border variant of halo_side (first strip's left side, last strip's right side): every column index is clamped /
+// reflected individually.  Rare, so kept out of line and un-unrolled to keep the hot code small.
+template <int C>
+__device__ __noinline__ void halo_side_border(const uint8_t *frame, int w, int h, int br, int xs, int side, float *dst, uint32_t *vh_out)
+{
+    const int ym = reflect101(br - 1, h), yp = reflect101(br + 1, h);
+    const int xb = side ? xs + STRIP_W : xs - 5;
+#pragma unroll 1
+    for (int k = 0; k < 5; ++k) {
+        const int cx = clampi(xb + k, w);
+        int sum = 0;
+#pragma unroll 1
+        for (int dx = -1; dx <= 1; ++dx) {
+            const int x = reflect101(cx + dx, w);
+            const int v = (int)grey_px<C>(frame, w, ym, x) + 2 * (int)grey_px<C>(frame, w, br, x) + (int)grey_px<C>(frame, w, yp, x);
+            sum += dx == 0 ? 2 * v : v;
+        }
+        dst[k] = (float)((sum + 8) >> 4);
+    }
+    const int xa = reflect101(side ? xs + STRIP_W : xs - 1, w);
+    *vh_out = (uint32_t)((int)grey_px<C>(frame, w, ym, xa) + 2 * (int)grey_px<C>(frame, w, br, xa) + (int)grey_px<C>(frame, w, yp, xa));
+}
+
 // Halo pass for one (step, side): blurred at the 5 columns next to the strip (clamped = BORDER_REPLICATE of the Gaussian;
 // neighbours with REFLECT_101 = border of the 3x3 blur) and the vertical sum of the adjacent column.
 template <int C>
@@ -259,11 +282,7 @@ __device__ __forceinline__ void halo_side(const uint8_t *frame, int w, int h, in
         for (int k = 0; k < 5; ++k) dst[k] = (float)((v[k] + 2 * v[k + 1] + v[k + 2] + 8) >> 4);
         *vh_out = (uint32_t)(side ? v[1] : v[5]);          // column xs+128 resp. xs-1
     } else {
-        for (int k = 0; k < 5; ++k) {
-            const int cx = clampi(xb + k, w);
-            dst[k] = (float)((vsum(reflect101(cx - 1, w)) + 2 * vsum(cx) + vsum(reflect101(cx + 1, w)) + 8) >> 4);
-        }
-        *vh_out = (uint32_t)vsum(reflect101(side ? xs + STRIP_W : xs - 1, w));
+        halo_side_border<C>(frame, w, h, br, xs, side, dst, vh_out);
     }
 }
 
@@ -280,10 +299,13 @@ __device__ __forceinline__ void strip_run(const FrontParams &p, const StripTask 
     const bool fast = aligned && (x0 + 3 < w);
     const bool row_tail = EDGE && (x0 >= p.row_tail_from);
     const bool col_tail = EDGE && (x0 >= p.col_tail_from);
-    uint32_t valid_nib = 0;
+    uint32_t valid_nib = 0xFu;                // interior strips: all four pixels of every lane are inside the image
+    if (EDGE) {
+        valid_nib = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) valid_nib |= (x0 + k < w) ? (1u << k) : 0u;
-    const uint32_t inv_nib = p.inverted ? 0xFu : 0u;
+        for (int k = 0; k < 4; ++k) valid_nib |= (x0 + k < w) ? (1u << k) : 0u;
+    }
+    const uint32_t inv_nib = (p.inverted ? 0xFu : 0u) & valid_nib;
     const int shift = 4 * (lane & 7);
     const int word = (xs >> 5) + (lane >> 3);
     const bool scalar_mode = p.scalar_thr != nullptr;
@@ -310,9 +332,11 @@ __device__ __forceinline__ void strip_run(const FrontParams &p, const StripTask 
     uint32_t gc = load_grey4<C>(frame, w, cbr, x0, fast);
     uint32_t gn = load_grey4<C>(frame, w, reflect101(cbr + 1, h), x0, fast);
     uint32_t pre = 0;
-    uint32_t *out_mask = p.mask_bits + ((int64_t)t.frame * h) * p.ww + word;
-    uint32_t *out_mark = p.marker_bits ? p.marker_bits + ((int64_t)t.frame * h) * p.ww + word : nullptr;
+    // output pointers of row y0 - 10 + s (advance by one row per step; only dereferenced for s >= 10)
+    uint32_t *out_mask = p.mask_bits + ((int64_t)t.frame * h + (t.y0 - 10)) * p.ww + word;
+    uint32_t *out_mark = p.marker_bits ? p.marker_bits + ((int64_t)t.frame * h + (t.y0 - 10)) * p.ww + word : nullptr;
     const bool writer = (lane & 7) == 0 && word < p.ww;
+    const int ww = p.ww;
 
     int j = 0;
     for (int s = 0; s < n_steps; ++s) {
@@ -398,17 +422,18 @@ __device__ __forceinline__ void strip_run(const FrontParams &p, const StripTask 
             const uint32_t y = (__byte_perm(lo, hi, 0x7531) >> 7) & 0x01010101u;
             return (y * 0x01020408u) >> 24;
         };
-        uint32_t nib_mask = (nibble(xa_lo, xa_hi) ^ inv_nib) & valid_nib;
-        uint32_t nib_mark = (nibble(xb_lo, xb_hi) ^ inv_nib) & valid_nib;
+        uint32_t nib_mask = (nibble(xa_lo, xa_hi) & valid_nib) ^ inv_nib;
+        uint32_t nib_mark = (nibble(xb_lo, xb_hi) & valid_nib) ^ inv_nib;
         uint32_t wm = nib_mask << shift, wk = nib_mark << shift;
         wm |= __shfl_xor_sync(0xffffffffu, wm, 1); wk |= __shfl_xor_sync(0xffffffffu, wk, 1);
         wm |= __shfl_xor_sync(0xffffffffu, wm, 2); wk |= __shfl_xor_sync(0xffffffffu, wk, 2);
         wm |= __shfl_xor_sync(0xffffffffu, wm, 4); wk |= __shfl_xor_sync(0xffffffffu, wk, 4);
         if (s >= 10 && writer) {
-            const int64_t o = (int64_t)(t.y0 + s - 10) * p.ww;
-            out_mask[o] = wm;
-            if (out_mark) out_mark[o] = wk;
+            *out_mask = wm;
+            if (out_mark) *out_mark = wk;
         }
+        out_mask += ww;
+        if (out_mark) out_mark += ww;
         // slide the grey window
         if (adv_next) { gp = gc; gc = gn; gn = pre; cbr = next_cbr; }
         j = j == 10 ? 0 : j + 1;
