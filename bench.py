@@ -198,39 +198,41 @@ def main():
         ctx.reset()
         return ctx.track_device(frames, 0, rows_capacity=rows_cap, rows_buf=rows_buf, return_device=True)
 
-    # multi-GPU: every rank detects its frame range; detections go to rank 0 which links all ranges in frame order
-    KEEP = 128            # detections per frame that travel (count is checked against it)
+    # multi-GPU: every rank detects its frame range; detection records are gathered over NCCL to rank 0, which runs the one
+    # sequential linker over all ranges in frame order (ysmr_b200/shard.py)
+    from ysmr_b200.shard import track_sharded
+    state = {}
+
+    def detect_range(a, b):                      # global frame indices; this rank holds [rank*F, (rank+1)*F)
+        lo = a - rank * F
+        counts = torch.empty(b - a, dtype=torch.int32, device=dev)
+        blobs = torch.empty((b - a, MB, 5), dtype=torch.float32, device=dev)
+        for i in range(0, b - a, args.batch):
+            j = min(b - a, i + args.batch)
+            c, bl = ctx.detect(frames[lo + i:lo + j], a + i)
+            counts[i:j] = c; blobs[i:j] = bl
+        return counts, blobs
+
+    def link_range(c, b, first):
+        import ctypes as C
+        if 'lctx' not in state or state['width'] != b.shape[1]:
+            state['lctx'] = Context(H, W, Cn, local, max_batch=8, max_blobs=int(b.shape[1]), max_tracks=MT)
+            state['width'] = int(b.shape[1])
+        l = state['lctx']
+        if first == 0:
+            l.reset(); state['total'] = 0
+        nr = torch.zeros(1, dtype=torch.int64, device=dev)
+        off = state['total'] * ROW_DTYPE.itemsize
+        l._check(l.lib.ysmr_link(l._h, C.c_void_p(c.data_ptr()), C.c_void_p(b.data_ptr()), int(first), int(c.numel()),
+                                 C.c_void_p(rows_buf.data_ptr() + off), rows_cap - state['total'],
+                                 C.c_void_p(nr.data_ptr()), l._stream_ptr()))
+        state['total'] += int(nr.item())
+        return None
+
     def step_multi():
-        counts = torch.empty(F, dtype=torch.int32, device=dev)
-        blobs = torch.empty((F, KEEP, 5), dtype=torch.float32, device=dev)
-        for a in range(0, F, args.batch):
-            b = min(F, a + args.batch)
-            c, bl = ctx.detect(frames[a:b], rank * F + a)
-            counts[a:b] = c; blobs[a:b] = bl[:, :KEEP]
-        gc = [torch.empty_like(counts) for _ in range(world)] if rank == 0 else None
-        gb = [torch.empty_like(blobs) for _ in range(world)] if rank == 0 else None
-        dist.gather(counts, gc, dst=0)
-        dist.gather(blobs, gb, dst=0)
+        track_sharded(world * F, world, rank, detect_range, link_range, 0, dist, dev)
         if rank == 0:
-            ctx.reset()
-            if not hasattr(step_multi, 'lctx'):
-                step_multi.lctx = Context(H, W, Cn, local, max_batch=8, max_blobs=KEEP, max_tracks=MT)
-            l = step_multi.lctx
-            l.reset()
-            n_rows = torch.zeros(1, dtype=torch.int64, device=dev)
-            total = 0
-            for r in range(world):
-                assert int(gc[r].max()) <= KEEP
-                # ysmr_link appends nothing across calls; rows of successive ranges go to successive slices
-                import ctypes as C
-                nr = torch.zeros(1, dtype=torch.int64, device=dev)
-                off = total * ROW_DTYPE.itemsize
-                l._check(l.lib.ysmr_link(l._h, C.c_void_p(gc[r].data_ptr()), C.c_void_p(gb[r].data_ptr()), r * F, F,
-                                         C.c_void_p(rows_buf.data_ptr() + off), rows_cap - total,
-                                         C.c_void_p(nr.data_ptr()), l._stream_ptr()))
-                total += int(nr.item())
-            n_rows[0] = total
-            return rows_buf, n_rows
+            return rows_buf, torch.tensor([state['total']], dtype=torch.int64, device=dev)
         return None, None
 
     step = step_single if world == 1 else step_multi
@@ -260,8 +262,8 @@ def main():
     prof = ctx.get_profile()
     ctx.set_profiling(False)
     launches = ctx.launch_count() - launches0
-    if world > 1 and rank == 0 and hasattr(step_multi, 'lctx'):
-        launches += step_multi.lctx.launch_count()
+    if world > 1 and rank == 0 and 'lctx' in state:
+        launches += state['lctx'].launch_count()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -1,0 +1,72 @@
+"""-m gpu: the sharded multi-GPU path against the single-GPU path (needs >= 2 GPUs; skipped otherwise).  One process per
+GPU, NCCL; rows must be bit-identical to the single-GPU rows."""
+import os
+import socket
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip('torch')
+
+
+def _free_port():
+    s = socket.socket(); s.bind(('127.0.0.1', 0)); p = s.getsockname()[1]; s.close()
+    return p
+
+
+def _frames():
+    from ysmr_b200.synth import SceneConfig, make_scene, render_frames
+    return render_frames(make_scene(SceneConfig(width=320, height=240, n_frames=150, n_cells=14, seed=3, margin=30.0)))
+
+
+def _run_single(grey):
+    from ysmr_b200.api import Context
+    ctx = Context(240, 320, 1, 0, max_batch=32, max_blobs=256, max_tracks=512)
+    rows = ctx.track_device(torch.from_numpy(grey).cuda(), 0)
+    ctx.close()
+    return rows
+
+
+def _worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    from ysmr_b200.api import Context
+    from ysmr_b200.shard import track_sharded
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dev = torch.device('cuda', rank)
+    dist.init_process_group('nccl', rank=rank, world_size=world, device_id=dev)
+    grey = _frames()
+    ctx = Context(240, 320, 1, rank, max_batch=32, max_blobs=256, max_tracks=512)
+
+    def detect_range(a, b):
+        fr = torch.from_numpy(grey[a:b]).to(dev)
+        cs, bs = [], []
+        for i in range(0, b - a, 32):
+            c, bl = ctx.detect(fr[i:i + 32], a + i)
+            cs.append(c); bs.append(bl)
+        return torch.cat(cs), torch.cat(bs)
+
+    link_ctx = {}
+
+    def link_range(c, b, first):
+        if 'l' not in link_ctx:
+            link_ctx['l'] = Context(240, 320, 1, rank, max_batch=4, max_blobs=int(b.shape[1]), max_tracks=512)
+        return link_ctx['l'].link(c, b, first, rows_capacity=int(c.numel()) * 512)
+
+    rows = track_sharded(len(grey), world, rank, detect_range, link_range, 0, dist, dev)
+    if rank == 0:
+        np.save(out_path, np.concatenate(rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_gpu_rows_bit_identical_to_one_gpu(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    import torch.multiprocessing as mp
+    out = str(tmp_path / 'rows.npy')
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = np.load(out)
+    ref = _run_single(_frames())
+    assert got.tobytes() == ref.tobytes()

@@ -1,0 +1,92 @@
+"""``ysmr()`` / ``analyse()`` with the reference's signatures (ysmr/main.py:32-172, 175-331), routing videos to the B200
+``track_bacteria``.
+
+The stages after tracking (select_tracks, evaluate_tracks, annotate_video -- SURVEY section 2, rows 7-9) are out of scope
+of this repository and are NOT re-implemented: when the reference package ``ysmr`` is importable, :func:`install`
+rebinds its ``track_bacteria`` to ours and these wrappers simply call the reference's own drivers, so every later stage,
+log line and file of the reference is produced by the reference's code on our ``_list.csv``.  Without the reference
+package the wrappers run the tracking stage only and keep the return conventions (DataFrame / True / None; list of
+``(path, result)``).
+"""
+from __future__ import annotations
+
+import logging
+import os
+
+from .settings import get_configs
+from .track_eval import track_bacteria
+
+__all__ = ['ysmr', 'analyse', 'install', 'uninstall']
+
+_saved = {}
+
+
+def install():
+    """Make the reference use the GPU path: rebinds ``ysmr.main.track_bacteria`` (imported by name at main.py:27) and
+    ``ysmr.track_eval.track_bacteria``.  Returns True when the reference package was found."""
+    try:
+        import ysmr.main as ref_main
+        import ysmr.track_eval as ref_te
+    except Exception:
+        return False
+    if 'main' not in _saved:
+        _saved['main'] = ref_main.track_bacteria
+        _saved['te'] = ref_te.track_bacteria
+    ref_main.track_bacteria = track_bacteria
+    ref_te.track_bacteria = track_bacteria
+    return True
+
+
+def uninstall():
+    if 'main' in _saved:
+        import ysmr.main as ref_main
+        import ysmr.track_eval as ref_te
+        ref_main.track_bacteria = _saved.pop('main')
+        ref_te.track_bacteria = _saved.pop('te')
+
+
+def analyse(path, settings=None, result_folder=None, return_df=False, **kwargs):
+    if install():
+        import ysmr.main as ref_main
+        return ref_main.analyse(path, settings=settings, result_folder=result_folder, return_df=return_df, **kwargs)
+    logger = logging.getLogger('ysmr').getChild(__name__)
+    settings = get_configs(settings)
+    if settings is None:
+        return None
+    if result_folder is None:
+        result_folder = os.path.dirname(os.path.abspath(path))
+    if any(ext in path for ext in ('_analysed.csv', '_statistics.csv', '_annotated_output.')):
+        logger.warning('File already evaluated. File: {}'.format(path))
+        return None
+    if '.csv' in path:
+        logger.warning('Only the tracking stage is available without the reference package; got a .csv: {}'.format(path))
+        return None
+    res = track_bacteria(video_path=path, settings=settings, result_folder=result_folder)
+    if res is None:
+        logger.warning('Error during video analysis of file {}.'.format(path))
+        return None
+    if settings.get('delete .csv file after analysis'):
+        try:
+            os.remove(res[4])
+        except OSError:
+            pass
+    return res[0] if return_df else True
+
+
+def ysmr(paths=None, settings=None, result_folder=None, multiprocess=False):
+    if install():
+        import ysmr.main as ref_main
+        # process-per-video (main.py:281-288) would need the rebinding in every child; videos are GPU-bound anyway
+        return ref_main.ysmr(paths=paths, settings=settings, result_folder=result_folder, multiprocess=False)
+    settings = get_configs(settings)
+    if settings is None:
+        print('Fatal error in retrieving tracking.ini')
+        return None
+    if isinstance(paths, (str, os.PathLike)):
+        paths = [paths]
+    if not paths:
+        return None
+    finished = []
+    for p in [os.path.expanduser(q) for q in paths]:
+        finished.append((p, analyse(p, settings=settings, result_folder=result_folder)))
+    return finished
