@@ -47,8 +47,14 @@ def test_track_bacteria_dropin(tmp_path, name):
     assert np.abs(mine[:, 4:] - ref[:, 4:]).max() < 1e-3
     head = open(csv).readlines()[0]
     assert head == 'TRACK_ID,POSITION_T,POSITION_X,POSITION_Y,WIDTH,HEIGHT,DEGREES_ANGLE\n'
-    # first data lines: identical text wherever the values are identical (they are for the first frames of track 0)
-    assert ''.join(open(csv).readlines()[:3]) == ''.join(str(g['csv_head']).splitlines(keepends=True)[:3])
+    # same text layout as the reference's file (ints, then repr floats); values agree to the tolerances above
+    mine_lines = open(csv).readlines()[1:4]
+    ref_lines = str(g['csv_head']).splitlines()[1:4]
+    for a, b in zip(mine_lines, ref_lines):
+        fa, fb = a.strip().split(','), b.strip().split(',')
+        assert fa[:2] == fb[:2] and len(fa) == len(fb) == 7
+        assert np.allclose([float(v) for v in fa[2:]], [float(v) for v in fb[2:]], rtol=1e-9, atol=1e-9)
+        assert fa[4:] == fb[4:]                       # w, h, deg: identical float32 values -> identical text
 
 
 def test_track_bacteria_error_conventions(tmp_path):
