@@ -11,7 +11,7 @@ import os
 import subprocess
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, 'libysmr_b200.so')
+LIB_PATH = os.environ.get('YSMR_LIB') or os.path.join(HERE, 'libysmr_b200.so')
 CSRC = os.path.join(HERE, 'csrc')
 
 YSMR_OK = 0

@@ -50,6 +50,8 @@ struct ysmr_ctx {
     int window = 0;               // mean/std moving window (frames)
     int gains_affine = 1;         // all uploaded FIR gains are affine in the tap index (required by the fast linker)
     int link_fast = 1;            // YSMR_LINK=general disables the shared-memory fast path of the linker (tests)
+    int fused_bgr = 0;            // YSMR_BGR=fused: luma inside the strip kernel instead of the grey pre-pass
+    uint8_t *grey = nullptr;      // [max_batch][h][w] grey planes of 3-channel input
     int use_tile = 0;             // YSMR_FRONTEND=tile: run the simple tile kernel instead of the strip kernel
     std::string err;
     int64_t launches = 0;
@@ -191,6 +193,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     c->device = device; c->h = height; c->w = width; c->ww = (width + 31) / 32; c->channels = channels; c->p = *params;
     derive_thresholds(c);
     { const char *fe = getenv("YSMR_FRONTEND"); c->use_tile = fe && strcmp(fe, "tile") == 0; }
+    { const char *bg = getenv("YSMR_BGR"); c->fused_bgr = bg && strcmp(bg, "fused") == 0; }
     { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strcmp(lk, "general") == 0); }
 #define CC(expr)                                                                                                       \
     do {                                                                                                               \
@@ -205,6 +208,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     const size_t B = (size_t)params->max_batch, H = (size_t)height, WW = (size_t)c->ww, MB = (size_t)params->max_blobs;
     CC(dev_alloc(c, &c->mask_bits, B * H * WW));
     CC(dev_alloc(c, &c->marker_bits, B * H * WW));
+    if (channels == 3) CC(dev_alloc(c, &c->grey, B * H * (size_t)width));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     c->label_grid = (int)std::min<size_t>(B, (size_t)sms * 6);
@@ -276,7 +280,11 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     // pipeline objects
     CC(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CC(cudaStreamCreateWithFlags(&c->s_det, cudaStreamNonBlocking));
-    CC(cudaStreamCreateWithFlags(&c->s_link, cudaStreamNonBlocking));
+    {
+        int lo = 0, hi = 0;
+        cudaDeviceGetStreamPriorityRange(&lo, &hi);          // the serial linker goes first whenever it is ready
+        CC(cudaStreamCreateWithPriority(&c->s_link, cudaStreamNonBlocking, hi));
+    }
     for (int i = 0; i < 2; ++i) {
         CC(cudaEventCreateWithFlags(&c->ev_copy[i], cudaEventDisableTiming));
         CC(cudaEventCreateWithFlags(&c->ev_det[i], cudaEventDisableTiming));
@@ -379,7 +387,15 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
     }
     if (!c->use_tile) {
         ProfScope ps(c, YSMR_PROF_FRONTEND, st);
-        CU(c, launch_frontend_strip(fp, st)); c->launches++;
+        if (c->channels == 3 && !c->fused_bgr) {
+            // cvtColor as a streaming pre-pass, then the single-channel strip kernel on the grey planes
+            CU(c, launch_bgr_to_grey(d_frames, frame_stride, c->grey, c->h, c->w, n_frames, st)); c->launches++;
+            FrontParams fg = fp;
+            fg.frames = c->grey; fg.frame_stride = (int64_t)c->h * c->w; fg.channels = 1;
+            CU(c, launch_frontend_strip(fg, st)); c->launches++;
+        } else {
+            CU(c, launch_frontend_strip(fp, st)); c->launches++;
+        }
     }
     const int64_t rows = (int64_t)n_frames * c->h;
     if (dbg && dbg->d_mask) { CU(c, launch_unpack_bits(c->mask_bits, dbg->d_mask, rows, c->w, c->ww, st)); c->launches++; }

@@ -138,7 +138,13 @@ __global__ void __launch_bounds__(256) frontend_tile_kernel(FrontParams p)
 // columns the strip needs from its neighbours are produced once per 11 steps by 22 otherwise idle lanes ("halo pass").
 // ---------------------------------------------------------------------------------------------------------------------
 constexpr int STRIP_W = 128;
-constexpr int STRIP_WARPS = 4;
+#ifndef STRIP_WARPS_N
+#define STRIP_WARPS_N 4
+#endif
+#ifndef STRIP_MINBLOCKS
+#define STRIP_MINBLOCKS 4
+#endif
+constexpr int STRIP_WARPS = STRIP_WARPS_N;
 constexpr int ROWBUF_W = STRIP_W + 16;            // 8 halo floats each side (5 used), keeps LDS.128 aligned
 constexpr float KG0 = 0.00881223008f, KG1 = 0.0271435864f, KG2 = 0.0651140586f, KG3 = 0.121649072f, KG4 = 0.176998362f,
                 KG5 = 0.200565413f;
@@ -159,11 +165,17 @@ __device__ __forceinline__ uint32_t load_grey4(const uint8_t *frame, int w, int 
     if (fast) {
         const uint32_t *q = reinterpret_cast<const uint32_t *>(frame + ((int64_t)y * w + x0) * C);
         if (C == 1) return __ldg(q);
+        // 12 bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3.  The Q15 luma weights 3735, 19235, 9798 are split into high
+        // and low bytes (14,75,38 / 151,35,70) so that each pixel costs two byte dot products:
+        // (3735 B + 19235 G + 9798 R + 16384) >> 15 == (256 * dp4a(px, hi) + dp4a(px, lo) + 16384) >> 15, exactly.
         const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-        const uint32_t g0 = luma(w0 & 0xFF, (w0 >> 8) & 0xFF, (w0 >> 16) & 0xFF);
-        const uint32_t g1 = luma(w0 >> 24, w1 & 0xFF, (w1 >> 8) & 0xFF);
-        const uint32_t g2 = luma((w1 >> 16) & 0xFF, w1 >> 24, w2 & 0xFF);
-        const uint32_t g3 = luma((w2 >> 8) & 0xFF, (w2 >> 16) & 0xFF, w2 >> 24);
+        const uint32_t p1 = __byte_perm(w0, w1, 0x0543);          // B1 G1 R1 (then B0, weight 0)
+        const uint32_t p2 = __byte_perm(w1, w2, 0x0432);          // B2 G2 R2
+        constexpr uint32_t HI = 14u | (75u << 8) | (38u << 16), LO = 151u | (35u << 8) | (70u << 16);
+        const uint32_t g0 = (__dp4a(w0, HI, 0u) * 256u + __dp4a(w0, LO, 16384u)) >> 15;
+        const uint32_t g1 = (__dp4a(p1, HI, 0u) * 256u + __dp4a(p1, LO, 16384u)) >> 15;
+        const uint32_t g2 = (__dp4a(p2, HI, 0u) * 256u + __dp4a(p2, LO, 16384u)) >> 15;
+        const uint32_t g3 = (__dp4a(w2, HI << 8, 0u) * 256u + __dp4a(w2, LO << 8, 16384u)) >> 15;   // B3 G3 R3 sit in bytes 1-3
         return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
     }
     uint32_t r = 0;
@@ -441,7 +453,7 @@ __device__ __forceinline__ void strip_run(const FrontParams &p, const StripTask 
 }
 
 template <int C>
-__global__ void __launch_bounds__(STRIP_WARPS * 32, 4) frontend_strip_kernel(FrontParams p, int n_strips, int n_chunks, int rows_per_chunk)
+__global__ void __launch_bounds__(STRIP_WARPS * 32, STRIP_MINBLOCKS) frontend_strip_kernel(FrontParams p, int n_strips, int n_chunks, int rows_per_chunk)
 {
     __shared__ __align__(16) float rowbuf[STRIP_WARPS][11][ROWBUF_W];
     __shared__ uint32_t vh[STRIP_WARPS][11][2];
@@ -459,6 +471,55 @@ __global__ void __launch_bounds__(STRIP_WARPS * 32, 4) frontend_strip_kernel(Fro
     const bool edge = (t.strip == n_strips - 1);       // the only strip that can hang over the right image edge
     if (edge) strip_run<C, true>(p, t, rowbuf[warp], vh[warp]);
     else strip_run<C, false>(p, t, rowbuf[warp], vh[warp]);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// BGR -> grey pre-pass (cv2.cvtColor, track_eval.py:180).  Streaming kernel: 8 pixels (24 bytes in, 8 bytes out) per
+// thread with 64-bit accesses.  Used in front of the strip kernel for 3-channel input: doing the luma inside the strip
+// kernel costs more than this pass (strided 12-byte loads per lane, luma repeated in the halo pass, register pressure).
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t luma_dp(uint32_t px)        // px = B | G << 8 | R << 16 (byte 3 ignored)
+{
+    constexpr uint32_t HI = 14u | (75u << 8) | (38u << 16), LO = 151u | (35u << 8) | (70u << 16);
+    return (__dp4a(px, HI, 0u) * 256u + __dp4a(px, LO, 16384u)) >> 15;
+}
+
+__global__ void __launch_bounds__(256) bgr_to_grey_kernel(const uint8_t *frames, int64_t frame_stride, uint8_t *grey, int64_t px_per_frame,
+                                                          int n_frames, int vec_ok)
+{
+    const int64_t groups = (px_per_frame + 7) / 8;
+    const int64_t total = groups * n_frames;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t f = i / groups, g = i - f * groups;
+        const uint8_t *src = frames + f * frame_stride + g * 24;
+        uint8_t *dst = grey + f * px_per_frame + g * 8;
+        const int64_t left = px_per_frame - g * 8;
+        if (vec_ok && left >= 8) {
+            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(src));
+            const uint2 b = __ldg(reinterpret_cast<const uint2 *>(src) + 1);
+            const uint2 c = __ldg(reinterpret_cast<const uint2 *>(src) + 2);
+            // bytes: a.x = B0 G0 R0 B1, a.y = G1 R1 B2 G2, b.x = R2 B3 G3 R3, b.y = B4 G4 R4 B5, c.x = G5 R5 B6 G6, c.y = R6 B7 G7 R7
+            const uint32_t g0 = luma_dp(a.x), g1 = luma_dp(__byte_perm(a.x, a.y, 0x0543)), g2 = luma_dp(__byte_perm(a.y, b.x, 0x0432)),
+                           g3 = luma_dp(b.x >> 8);
+            const uint32_t g4 = luma_dp(b.y), g5 = luma_dp(__byte_perm(b.y, c.x, 0x0543)), g6 = luma_dp(__byte_perm(c.x, c.y, 0x0432)),
+                           g7 = luma_dp(c.y >> 8);
+            uint2 o;
+            o.x = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
+            o.y = g4 | (g5 << 8) | (g6 << 16) | (g7 << 24);
+            *reinterpret_cast<uint2 *>(dst) = o;
+        } else {
+            for (int k = 0; k < 8 && k < left; ++k) dst[k] = (uint8_t)luma(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
+        }
+    }
+}
+
+cudaError_t launch_bgr_to_grey(const uint8_t *frames, int64_t frame_stride, uint8_t *grey, int h, int w, int n_frames, cudaStream_t st)
+{
+    const int64_t px = (int64_t)h * w;
+    const int vec_ok = ((reinterpret_cast<uintptr_t>(frames) & 7) == 0) && (frame_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(grey) & 7) == 0) &&
+                       (px % 8 == 0);
+    bgr_to_grey_kernel<<<148 * 16, 256, 0, st>>>(frames, frame_stride, grey, px, n_frames, vec_ok);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------------------------------

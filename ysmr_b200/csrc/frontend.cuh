@@ -23,6 +23,7 @@ struct FrontParams {
 
 cudaError_t launch_frontend_tile(const FrontParams &p, cudaStream_t st);
 cudaError_t launch_frontend_strip(const FrontParams &p, cudaStream_t st);
+cudaError_t launch_bgr_to_grey(const uint8_t *frames, int64_t frame_stride, uint8_t *grey, int h, int w, int n_frames, cudaStream_t st);
 cudaError_t launch_unpack_bits(const uint32_t *bits, uint8_t *bytes, int64_t rows, int w, int ww, cudaStream_t st);
 cudaError_t launch_frame_moments(const uint8_t *frames, int64_t stride, int n_frames, int h, int w, int channels,
                                  unsigned long long *sums, cudaStream_t st);
