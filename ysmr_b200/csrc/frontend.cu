@@ -211,6 +211,49 @@ __device__ __forceinline__ float gauss_row(const float *a, bool tail)
     return acc;
 }
 
+// Blackwell packed FP32: one instruction, two IEEE-rounded results (SASS FFMA2 / FMUL2 / FADD2).  Element-wise identical
+// to the scalar operations, so the bit-exactness argument is unchanged; it halves the issue slots of the column pass.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c)
+{
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rc, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mov.b64 rc, {%6, %7};\n"
+        " fma.rn.f32x2 rd, ra, rb, rc;\n mov.b64 {%0, %1}, rd; }\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fadd2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n add.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd; }\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b)
+{
+    float2 d;
+    asm("{ .reg .b64 ra, rb, rd;\n mov.b64 ra, {%2, %3};\n mov.b64 rb, {%4, %5};\n mul.rn.f32x2 rd, ra, rb;\n mov.b64 {%0, %1}, rd; }\n"
+        : "=f"(d.x), "=f"(d.y) : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+
+// column pass for two adjacent pixels at once
+template <bool TAIL>
+__device__ __forceinline__ float2 gauss_col2(float2 c, float2 m1, float2 p1, float2 m2, float2 p2, float2 m3, float2 p3, float2 m4,
+                                             float2 p4, float2 m5, float2 p5, bool tail)
+{
+    const float2 k5 = make_float2(KG5, KG5), k4 = make_float2(KG4, KG4), k3 = make_float2(KG3, KG3), k2 = make_float2(KG2, KG2),
+                 k1 = make_float2(KG1, KG1), k0 = make_float2(KG0, KG0);
+    float2 acc = fmul2(k5, c);
+    const float2 s1 = fadd2(m1, p1), s2 = fadd2(m2, p2), s3 = fadd2(m3, p3), s4 = fadd2(m4, p4), s5 = fadd2(m5, p5);
+    if (TAIL && tail) {
+        acc = fadd2(acc, fmul2(k4, s1)); acc = fadd2(acc, fmul2(k3, s2)); acc = fadd2(acc, fmul2(k2, s3));
+        acc = fadd2(acc, fmul2(k1, s4)); acc = fadd2(acc, fmul2(k0, s5));
+        return acc;
+    }
+    acc = ffma2(k4, s1, acc); acc = ffma2(k3, s2, acc); acc = ffma2(k2, s3, acc); acc = ffma2(k1, s4, acc); acc = ffma2(k0, s5, acc);
+    return acc;
+}
+
 template <bool TAIL>
 __device__ __forceinline__ float gauss_col(float c, float m1, float p1, float m2, float p2, float m3, float p3, float m4,
                                            float p4, float m5, float p5, bool tail)
@@ -238,19 +281,20 @@ struct StripTask {
 // caller dispatches on (step % 11) with a switch, which keeps the rest of the step loop un-unrolled (a fully unrolled
 // body would be ~45 KB of code and thrash the instruction cache).
 template <int J, bool TAIL>
-__device__ __forceinline__ void window_step(float (&win)[11][4], uint32_t (&bq)[11], const float (&r)[4], uint32_t bcur,
+__device__ __forceinline__ void window_step(float2 (&win)[11][2], uint32_t (&bq)[11], const float (&r)[4], uint32_t bcur,
                                             bool col_tail, float (&m)[4], uint32_t &bc)
 {
     constexpr int c = (J + 6) % 11;            // (J - 5) mod 11
-#pragma unroll
-    for (int k = 0; k < 4; ++k) win[J][k] = r[k];
+    win[J][0] = make_float2(r[0], r[1]); win[J][1] = make_float2(r[2], r[3]);
     bq[J] = bcur;                              // blurred px0..px3 as bytes
     bc = bq[c];
 #pragma unroll
-    for (int k = 0; k < 4; ++k)
-        m[k] = gauss_col<TAIL>(win[c][k], win[(c + 10) % 11][k], win[(c + 1) % 11][k], win[(c + 9) % 11][k], win[(c + 2) % 11][k],
-                               win[(c + 8) % 11][k], win[(c + 3) % 11][k], win[(c + 7) % 11][k], win[(c + 4) % 11][k],
-                               win[(c + 6) % 11][k], win[(c + 5) % 11][k], col_tail);
+    for (int k = 0; k < 2; ++k) {
+        const float2 v = gauss_col2<TAIL>(win[c][k], win[(c + 10) % 11][k], win[(c + 1) % 11][k], win[(c + 9) % 11][k],
+                                          win[(c + 2) % 11][k], win[(c + 8) % 11][k], win[(c + 3) % 11][k], win[(c + 7) % 11][k],
+                                          win[(c + 4) % 11][k], win[(c + 6) % 11][k], win[(c + 5) % 11][k], col_tail);
+        m[2 * k] = v.x; m[2 * k + 1] = v.y;
+    }
 }
 
 // Image-border variant of halo_side (first strip's left side, last strip's right side): every column index is clamped /
@@ -333,10 +377,10 @@ __device__ __forceinline__ void strip_run(const FrontParams &p, const StripTask 
     // REPLICATE source for pixels right of the image (EDGE strips only)
     const int e_owner = (w - 1 - xs) >> 2, e_pos = (w - 1 - xs) & 3;
 
-    float win[11][4];                 // row-pass results of the last 11 steps
+    float2 win[11][2];                // row-pass results of the last 11 steps, as pixel pairs (px0,px1), (px2,px3)
     uint32_t bq[11];                  // blurred (u8x4) of the last 11 steps
 #pragma unroll
-    for (int i = 0; i < 11; ++i) { bq[i] = 0; win[i][0] = win[i][1] = win[i][2] = win[i][3] = 0.f; }
+    for (int i = 0; i < 11; ++i) { bq[i] = 0; win[i][0] = win[i][1] = make_float2(0.f, 0.f); }
 
     const int n_steps = (t.y1 - t.y0) + 10;
     int cbr = clampi(t.y0 - 5, h);    // clamped blurred row of the current step
