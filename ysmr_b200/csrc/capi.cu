@@ -52,7 +52,10 @@ struct ysmr_ctx {
     int link_fast = 1;            // YSMR_LINK=general disables the shared-memory fast path of the linker (tests)
     int fused_bgr = 0;            // YSMR_BGR=fused: luma inside the strip kernel instead of the grey pre-pass
     uint8_t *grey = nullptr;      // [max_batch][h][w] grey planes of 3-channel input
-    int use_tile = 0;             // YSMR_FRONTEND=tile: run the simple tile kernel instead of the strip kernel
+    int use_tile = 0;             // YSMR_FRONTEND=tile: run the simple tile kernel instead of the production kernels
+    int use_strip = 0;            // YSMR_FRONTEND=strip: previous-generation strip kernel (kept for A/B timing)
+    uint8_t *plane = nullptr; int64_t plane_stride = 0; int pitch = 0;          // blurred planes (K1a -> K1b)
+    uint8_t *decisions = nullptr; int64_t dec_stride = 0; int dec_pitch = 0;    // decision bytes (K1b -> K1c)
     std::string err;
     int64_t launches = 0;
 
@@ -192,7 +195,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     ysmr_ctx *c = new ysmr_ctx();
     c->device = device; c->h = height; c->w = width; c->ww = (width + 31) / 32; c->channels = channels; c->p = *params;
     derive_thresholds(c);
-    { const char *fe = getenv("YSMR_FRONTEND"); c->use_tile = fe && strcmp(fe, "tile") == 0; }
+    { const char *fe = getenv("YSMR_FRONTEND"); c->use_tile = fe && strcmp(fe, "tile") == 0; c->use_strip = fe && strcmp(fe, "strip") == 0; }
     { const char *bg = getenv("YSMR_BGR"); c->fused_bgr = bg && strcmp(bg, "fused") == 0; }
     { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strcmp(lk, "general") == 0); }
 #define CC(expr)                                                                                                       \
@@ -208,7 +211,14 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     const size_t B = (size_t)params->max_batch, H = (size_t)height, WW = (size_t)c->ww, MB = (size_t)params->max_blobs;
     CC(dev_alloc(c, &c->mask_bits, B * H * WW));
     CC(dev_alloc(c, &c->marker_bits, B * H * WW));
-    if (channels == 3) CC(dev_alloc(c, &c->grey, B * H * (size_t)width));
+    if (channels == 3 && c->use_strip) CC(dev_alloc(c, &c->grey, B * H * (size_t)width));
+    c->pitch = 16 + ((width + 127) / 128) * 128;
+    c->plane_stride = (int64_t)(height + 10) * c->pitch;
+    CC(dev_alloc(c, &c->plane, B * (size_t)c->plane_stride));
+    CC(cudaMemset(c->plane, 0, B * (size_t)c->plane_stride));
+    c->dec_pitch = 32 * ((width + 127) / 128);
+    c->dec_stride = (int64_t)height * c->dec_pitch;
+    CC(dev_alloc(c, &c->decisions, B * (size_t)c->dec_stride));
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     c->label_grid = (int)std::min<size_t>(B, (size_t)sms * 6);
@@ -369,6 +379,8 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
     fp.marker_bits = c->mode == YSMR_MODE_ADAPTIVE_DOUBLE ? c->marker_bits : nullptr;
     memcpy(fp.k, kGaussBits, sizeof(fp.k));
     fp.row_tail_from = c->w - c->w % 4; fp.col_tail_from = c->w - c->w % 8;
+    fp.plane = c->plane; fp.plane_stride = c->plane_stride; fp.pitch = c->pitch;
+    fp.decisions = c->decisions; fp.dec_stride = c->dec_stride; fp.dec_pitch = c->dec_pitch;
     if (dbg) { fp.dbg_grey = dbg->d_grey; fp.dbg_blurred = dbg->d_blurred; fp.dbg_mean = dbg->d_mean; }
     if (c->mode == YSMR_MODE_MEAN_STD) {
         CU(c, launch_frame_moments(d_frames, frame_stride, n_frames, c->h, c->w, c->channels, c->sums, st));
@@ -385,7 +397,12 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
         ProfScope ps(c, c->use_tile ? YSMR_PROF_FRONTEND : YSMR_PROF_GEOMETRY, st);
         CU(c, launch_frontend_tile(fp, st)); c->launches++;
     }
-    if (!c->use_tile) {
+    if (!c->use_tile && !c->use_strip) {
+        ProfScope ps(c, YSMR_PROF_FRONTEND, st);
+        int nl = 0;
+        CU(c, launch_frontend_v3(fp, st, &nl)); c->launches += nl;
+    }
+    if (c->use_strip) {
         ProfScope ps(c, YSMR_PROF_FRONTEND, st);
         if (c->channels == 3 && !c->fused_bgr) {
             // cvtColor as a streaming pre-pass, then the single-channel strip kernel on the grey planes

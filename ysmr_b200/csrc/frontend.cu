@@ -517,16 +517,377 @@ __global__ void __launch_bounds__(STRIP_WARPS * 32, STRIP_MINBLOCKS) frontend_st
     else strip_run<C, false>(p, t, rowbuf[warp], vh[warp]);
 }
 
+// =====================================================================================================================
+// Production front-end, generation 3: three kernels
+//
+//   K1a blur_prepass_kernel   BGR/grey -> luma -> 3x3 binomial blur, written as a PADDED u8 plane (replicated margins), so
+//                             that the Gaussian kernel below has no border logic at all.  Integer work, HBM-bound.
+//   K1b gauss_decide_kernel   11x11 float32 Gaussian mean (OpenCV's operation order), rint, the two threshold decisions.
+//                             Everything after the u8->float conversion runs on the FP32 pipe (measured on B200: FFMA/FADD
+//                             issue 1/clk per SM sub-partition, every integer ALU op 1 per 2 clk, SHFL 1 per 4 clk --
+//                             scripts/ubench.cu), including the decisions (add.sat) and the packing of a lane's eight
+//                             decisions into one byte (FFMA chain onto 2^23).  Output: one "decision byte" per lane and row.
+//   K1c pack_masks_kernel     decision bytes -> the two standard bit masks (bit x&31 of word x>>5), polarity and width applied.
+//
+// Blurred plane of one frame: rows -5 .. h+4, `pitch` bytes each; pixel (x, y) at (y + 5) * pitch + 8 + x; columns -8..-1
+// and w..w+7 and the 5 rows above / below hold BORDER_REPLICATE copies (what cv2.adaptiveThreshold's Gaussian sees).
+// =====================================================================================================================
+__device__ __forceinline__ uint32_t luma_dp(uint32_t px)        // px = B | G << 8 | R << 16 (byte 3 ignored)
+{
+    // (3735 B + 19235 G + 9798 R + 16384) >> 15 with the weights split into high and low bytes: two byte dot products
+    constexpr uint32_t HI = 14u | (75u << 8) | (38u << 16), LO = 151u | (35u << 8) | (70u << 16);
+    return (__dp4a(px, HI, 0u) * 256u + __dp4a(px, LO, 16384u)) >> 15;
+}
+
+constexpr int PB_WARPS = 4;
+constexpr int PB_COLS = 256;                      // columns per warp of K1a: 8 adjacent pixels per lane
+
+struct GreyRow {                                   // one row of a lane: 8 pixels + 2 side pixels as 16-bit lanes
+    uint32_t p01, p23, p45, p67, side;
+};
+
+// Q15 luma (3735 B + 19235 G + 9798 R + 16384) >> 15 of a pixel whose three bytes sit anywhere in one or two words: two
+// 16-bit x 8-bit dot products (dp2a) with the weights arranged for the byte position, no byte shuffling.
+constexpr uint32_t LW_BG = 3735u | (19235u << 16), LW_R0 = 9798u, LW_0B = 3735u << 16, LW_GR = 19235u | (9798u << 16);
+__device__ __forceinline__ uint32_t luma_b012(uint32_t v) { return __dp2a_hi(LW_R0, v, __dp2a_lo(LW_BG, v, 16384u)) >> 15; }
+__device__ __forceinline__ uint32_t luma_b123(uint32_t v) { return __dp2a_hi(LW_GR, v, __dp2a_lo(LW_0B, v, 16384u)) >> 15; }
+__device__ __forceinline__ uint32_t luma_b3_01(uint32_t v, uint32_t n) { return __dp2a_lo(LW_GR, n, __dp2a_hi(LW_0B, v, 16384u)) >> 15; }
+__device__ __forceinline__ uint32_t luma_b23_0(uint32_t v, uint32_t n) { return __dp2a_lo(LW_R0, n, __dp2a_hi(LW_BG, v, 16384u)) >> 15; }
+
+// four BGR pixels (12 bytes = words w0, w1, w2) -> two pairs of 16-bit lanes
+__device__ __forceinline__ void luma4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t &pa, uint32_t &pb)
+{
+    pa = luma_b012(w0) | (luma_b3_01(w0, w1) << 16);
+    pb = luma_b23_0(w1, w2) | (luma_b123(w2) << 16);
+}
+
+// One row of a lane.  FAST: w % 4 == 0 and 4-byte aligned frames, so every lane inside the image loads whole 32-bit words and
+// REFLECT_101 at the left / right image border is done in registers; otherwise per-pixel loads (any width, slow).
+template <int C, bool FAST>
+__device__ __forceinline__ GreyRow load_row(const uint8_t *frame, int w, int y, int gx, int nvalid)
+{
+    GreyRow g;
+    if (FAST) {
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(frame + ((int64_t)y * w + gx) * C);
+        g.p45 = 0; g.p67 = 0;
+        uint32_t l = 0, r = 0;
+        if (C == 1) {
+            const uint32_t lo = __ldg(q);
+            g.p01 = __byte_perm(lo, 0, 0x4140); g.p23 = __byte_perm(lo, 0, 0x4342);
+            if (nvalid >= 8) {
+                const uint32_t hi = __ldg(q + 1);
+                g.p45 = __byte_perm(hi, 0, 0x4140); g.p67 = __byte_perm(hi, 0, 0x4342);
+            }
+            if (gx != 0) l = __ldg(q - 1) >> 24;
+            if (nvalid >= 8 && gx + 8 < w) r = __ldg(q + 2) & 0xFFu;
+        } else {
+            luma4(__ldg(q), __ldg(q + 1), __ldg(q + 2), g.p01, g.p23);
+            if (nvalid >= 8) luma4(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5), g.p45, g.p67);
+            if (gx != 0) l = luma_b123(__ldg(q - 1));
+            if (nvalid >= 8 && gx + 8 < w) r = luma_b012(__ldg(q + 6));
+        }
+        if (gx == 0) l = g.p01 >> 16;                              // REFLECT_101: column -1 is column 1
+        if (nvalid < 8) g.p45 = g.p23 & 0xFFFFu;                   // column w is column w-2 (w % 8 == 4)
+        else if (gx + 8 >= w) r = g.p67 & 0xFFFFu;                 // column w is column w-2 (w % 8 == 0)
+        g.side = l | (r << 16);
+    } else {
+        uint32_t v[10];
+#pragma unroll
+        for (int k = 0; k < 10; ++k) v[k] = grey_px<C>(frame, w, y, reflect101(gx - 1 + k, w));
+        g.p01 = v[1] | (v[2] << 16); g.p23 = v[3] | (v[4] << 16); g.p45 = v[5] | (v[6] << 16); g.p67 = v[7] | (v[8] << 16);
+        g.side = v[0] | (v[9] << 16);
+    }
+    return g;
+}
+
+__device__ __forceinline__ GreyRow add_rows(const GreyRow &a, const GreyRow &b)
+{
+    GreyRow s;
+    s.p01 = a.p01 + b.p01; s.p23 = a.p23 + b.p23; s.p45 = a.p45 + b.p45; s.p67 = a.p67 + b.p67; s.side = a.side + b.side;
+    return s;
+}
+
+template <int C, bool FAST>
+__global__ void __launch_bounds__(PB_WARPS * 32) blur_prepass_kernel(FrontParams p, int n_strips, int n_chunks, int rows_per_chunk)
+{
+    const int lane = threadIdx.x & 31;
+    const int64_t task = (int64_t)blockIdx.x * PB_WARPS + (threadIdx.x >> 5);
+    const int64_t per_frame = (int64_t)n_strips * n_chunks;
+    if (task >= per_frame * p.n_frames) return;
+    const int f = (int)(task / per_frame);
+    const int r = (int)(task - (int64_t)f * per_frame);
+    const int strip = r % n_strips, chunk = r / n_strips;
+    const int y0 = chunk * rows_per_chunk, y1 = min(p.h, y0 + rows_per_chunk);
+    const int w = p.w, h = p.h;
+    const uint8_t *frame = p.frames + (int64_t)f * p.frame_stride;
+    const int gx = strip * PB_COLS + 8 * lane;
+    if (gx >= w) return;                                          // no cross-lane traffic in this kernel
+    const int nvalid = FAST ? (w - gx >= 8 ? 8 : 4) : 8;
+    uint8_t *dst = p.plane + (int64_t)f * p.plane_stride + (int64_t)(y0 + 5) * p.pitch + 8 + gx;
+    const int pitch = p.pitch;
+
+    GreyRow a = load_row<C, FAST>(frame, w, reflect101(y0 - 1, h), gx, nvalid);
+    GreyRow b = load_row<C, FAST>(frame, w, y0, gx, nvalid);
+    GreyRow s_prev = add_rows(a, b);                              // S(y-1) = g(y-1) + g(y)
+    GreyRow nxt = load_row<C, FAST>(frame, w, reflect101(y0 + 1, h), gx, nvalid);
+    for (int y = y0; y < y1; ++y) {
+        const GreyRow c = nxt;
+        if (y + 1 < y1) nxt = load_row<C, FAST>(frame, w, reflect101(y + 2, h), gx, nvalid);     // prefetch
+        const GreyRow s_cur = add_rows(b, c);                     // S(y) = g(y) + g(y+1)
+        const GreyRow v = add_rows(s_prev, s_cur);                // vertical 1-2-1
+        s_prev = s_cur; b = c;
+        const uint32_t m0 = __byte_perm(v.side, v.p01, 0x5410);   // (v[-1], v0)
+        const uint32_t m1 = __byte_perm(v.p01, v.p23, 0x5432);    // (v1, v2)
+        const uint32_t m2 = __byte_perm(v.p23, v.p45, 0x5432);    // (v3, v4)
+        const uint32_t m3 = __byte_perm(v.p45, v.p67, 0x5432);    // (v5, v6)
+        const uint32_t m4 = __byte_perm(v.p67, v.side, 0x7632);   // (v7, v8)
+        const uint32_t o01 = (m0 + m1 + 0x00080008u + 2 * v.p01) >> 4;
+        const uint32_t o23 = (m1 + m2 + 0x00080008u + 2 * v.p23) >> 4;
+        const uint32_t o45 = (m2 + m3 + 0x00080008u + 2 * v.p45) >> 4;
+        const uint32_t o67 = (m3 + m4 + 0x00080008u + 2 * v.p67) >> 4;
+        uint2 out;
+        out.x = __byte_perm(o01, o23, 0x6420);
+        out.y = __byte_perm(o45, o67, 0x6420);
+        *reinterpret_cast<uint2 *>(dst) = out;
+        dst += pitch;
+    }
+}
+
+// Replicated margins of the blurred planes (BORDER_REPLICATE of cv2.adaptiveThreshold's Gaussian): columns -8..-1 and
+// w..w+7 of every image row, and the 5 rows above / below the image.  One work item per (frame, image row) plus one per
+// (frame, margin row, 32-bit word).
+__global__ void __launch_bounds__(256) plane_margins_kernel(FrontParams p)
+{
+    const int wpr = p.pitch / 4;                                  // words per plane row
+    const int64_t per_frame = (int64_t)p.h + 10 * (int64_t)wpr;
+    const int64_t total = per_frame * p.n_frames;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int f = (int)(i / per_frame);
+        const int64_t k = i - (int64_t)f * per_frame;
+        uint8_t *plane = p.plane + (int64_t)f * p.plane_stride;
+        if (k < p.h) {
+            uint8_t *row = plane + (k + 5) * (int64_t)p.pitch + 8;
+            const uint32_t l = row[0] * 0x01010101u, r = row[p.w - 1] * 0x01010101u;
+            reinterpret_cast<uint32_t *>(row)[-2] = l; reinterpret_cast<uint32_t *>(row)[-1] = l;
+            for (int x = p.w; x < p.w + 8; ++x) row[x] = (uint8_t)r;
+        } else {
+            const int64_t kk = k - p.h;
+            const int mr = (int)(kk / wpr), word = (int)(kk - (int64_t)mr * wpr);
+            const int dst_row = mr < 5 ? mr : p.h + 5 + (mr - 5);              // plane row index (image row + 5)
+            const int src_row = mr < 5 ? 5 : p.h + 4;
+            const uint8_t *src = plane + (int64_t)src_row * p.pitch + 8;
+            uint32_t v = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                int x = 4 * word + b - 8;
+                x = x < 0 ? 0 : (x >= p.w ? p.w - 1 : x);
+                v |= (uint32_t)src[x] << (8 * b);
+            }
+            reinterpret_cast<uint32_t *>(plane + (int64_t)dst_row * p.pitch)[word] = v;
+        }
+    }
+}
+
+// ---- K1b ------------------------------------------------------------------------------------------------------------
+// Work item = (frame, 128-column strip, row chunk), one per WARP; lane l owns columns x0 = xs + 4l .. +3.  Step s handles
+// blurred row y0 - 5 + s: LDG.32 -> four floats -> ring slot s & 7 of the warp's shared row buffer; 5 x LDS.128 give the 14
+// taps of the lane's four row-pass results, which enter an 11-row register window; the column pass around the row 5 steps
+// back gives the float mean of output row y0 + s - 10.  Decisions, all exact in float:
+//     R = mean + 1.5*2^23                      (rint, half to even, as an integer-valued float)
+//     d = sat((b + 1.5*2^23 - t) - R)          (1.0f iff b - rint(mean) > t ; both operands are integers < 2^24)
+// and the lane's byte = sum d_mask[k] 2^k + d_marker[k] 2^(4+k) accumulated onto 2^23 so that it is the low mantissa byte.
+// The 2 x 8 halo columns of a strip are converted by all 32 lanes at once for 8 rows every 8 steps.
+constexpr int GD_WARPS = 4;
+constexpr int GD_RING = 8;
+constexpr int GD_ROWF = 144;                      // floats per ring slot: 8 halo | 128 | 8 halo
+constexpr float GD_MAGIC = 12582912.0f;           // 1.5 * 2^23
+
+__device__ __forceinline__ float sub_sat(float a, float b)
+{
+    float d;
+    asm("sub.sat.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
+    return d;
+}
+
+__device__ __forceinline__ float4 u8x4_to_float4(uint32_t u)
+{
+    float4 f;
+    f.x = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7540)) - 8388608.0f;
+    f.y = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7541)) - 8388608.0f;
+    f.z = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7542)) - 8388608.0f;
+    f.w = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7543)) - 8388608.0f;
+    return f;
+}
+
+// One step of the register window: file this step's row-pass results in slot J and run the column pass centred 5 steps
+// back.  Only this part depends on J (static register indices), so only this part is replicated 11 times behind the switch
+// of the step loop -- the replicated code must stay small: with the whole step body inside the switch the kernel was bound by
+// instruction-cache misses (ncu: stall_no_instruction 1.9 warps per issue, icc hit rate 73 %).
+template <int J, bool TAIL>
+__device__ __forceinline__ void gd_window(float2 (&win)[11][2], const float (&r)[4], float (&m)[4], bool col_tail)
+{
+    constexpr int c = (J + 6) % 11;               // (J - 5) mod 11: window slot of the centre row
+    win[J][0] = make_float2(r[0], r[1]); win[J][1] = make_float2(r[2], r[3]);
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float2 v = gauss_col2<TAIL>(win[c][k], win[(c + 10) % 11][k], win[(c + 1) % 11][k], win[(c + 9) % 11][k], win[(c + 2) % 11][k],
+                                          win[(c + 8) % 11][k], win[(c + 3) % 11][k], win[(c + 7) % 11][k], win[(c + 4) % 11][k],
+                                          win[(c + 6) % 11][k], win[(c + 5) % 11][k], col_tail);
+        m[2 * k] = v.x; m[2 * k + 1] = v.y;
+    }
+}
+
+// lane's decision byte from the four float means and the four blurred values of the output row
+__device__ __forceinline__ uint32_t gd_decide(const float (&m)[4], const float4 bf, float c_mask, float c_mark)
+{
+    const float b[4] = {bf.x, bf.y, bf.z, bf.w};
+    float acc = 8388608.0f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const float r = __fadd_rn(m[k], GD_MAGIC);
+        const float d_mask = sub_sat(__fadd_rn(b[k], c_mask), r);
+        const float d_mark = sub_sat(__fadd_rn(b[k], c_mark), r);
+        acc = __fmaf_rn(d_mask, (float)(1 << k), acc);
+        acc = __fmaf_rn(d_mark, (float)(16 << k), acc);
+    }
+    return __float_as_uint(acc);
+}
+
+// TAIL = false: strips without scalar-tail columns (every column fused).  TAIL = true: the strip(s) that contain OpenCV's
+// scalar-tail columns (the last w % 8 columns of the column filter and the last w % 4 of the row filter are not
+// FMA-contracted); launched separately for those strips only so that the common code stays small.
+template <bool TAIL>
+__global__ void __launch_bounds__(GD_WARPS * 32, 4) gauss_decide_kernel(FrontParams p, int first_strip, int n_strips, int n_chunks, int rows_per_chunk)
+{
+    __shared__ __align__(16) float ring_all[GD_WARPS][GD_RING * GD_ROWF];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t task = (int64_t)blockIdx.x * GD_WARPS + warp;
+    const int64_t per_frame = (int64_t)n_strips * n_chunks;
+    if (task >= per_frame * p.n_frames) return;
+    const int f = (int)(task / per_frame);
+    const int rr = (int)(task - (int64_t)f * per_frame);
+    const int strip = first_strip + rr % n_strips, chunk = rr / n_strips;
+    const int y0 = chunk * rows_per_chunk, y1 = min(p.h, y0 + rows_per_chunk);
+    float *ring = ring_all[warp];
+
+    const int xs = strip * 128, x0 = xs + 4 * lane;
+    const int pitch = p.pitch;
+    const float c_mask = GD_MAGIC - (float)p.t_mask, c_mark = GD_MAGIC - (float)p.t_marker;
+    const bool row_tail = TAIL && x0 >= p.row_tail_from, col_tail = TAIL && x0 >= p.col_tail_from;
+    const uint8_t *src = p.plane + (int64_t)f * p.plane_stride + (int64_t)y0 * pitch + 8 + x0;      // row y0 - 5
+    // halo words of a row: lane & 3 -> columns xs-8, xs-4, xs+128, xs+132 ; lane >> 2 -> row within the group of 8
+    const int hj = lane & 3, hk = lane >> 2;
+    const uint8_t *hsrc = p.plane + (int64_t)f * p.plane_stride + (int64_t)(y0 + hk) * pitch + 8 + xs + (hj < 2 ? 4 * hj - 8 : 120 + 4 * hj);
+    float *hdst = ring + hk * GD_ROWF + (hj < 2 ? 4 * hj : 128 + 4 * hj);
+    uint8_t *dst = p.decisions + (int64_t)f * p.dec_stride + (int64_t)(y0 - 10) * p.dec_pitch + strip * 32 + lane;
+    const int dec_pitch = p.dec_pitch;
+    const int n_steps = (y1 - y0) + 10;
+
+    float2 win[11][2];
+#pragma unroll
+    for (int i = 0; i < 11; ++i) win[i][0] = win[i][1] = make_float2(0.f, 0.f);
+
+    uint32_t u0 = __ldg(reinterpret_cast<const uint32_t *>(src));
+    uint32_t u1 = n_steps > 1 ? __ldg(reinterpret_cast<const uint32_t *>(src + pitch)) : 0u;
+    src += 2 * (int64_t)pitch;
+    int j = 0;
+    for (int s = 0; s < n_steps; ++s) {
+        const int slot = s & (GD_RING - 1);
+        if (slot == 0) {
+            __syncwarp();                         // the row pass of the previous step has read the halo zones
+            if (s + hk < n_steps) {
+                const uint32_t hw = __ldg(reinterpret_cast<const uint32_t *>(hsrc));
+                *reinterpret_cast<float4 *>(hdst) = u8x4_to_float4(hw);
+            }
+            hsrc += GD_RING * (int64_t)pitch;
+        }
+        const uint32_t u = u0;
+        u0 = u1;
+        if (s + 2 < n_steps) u1 = __ldg(reinterpret_cast<const uint32_t *>(src));
+        src += pitch;
+        float *row = ring + slot * GD_ROWF;
+        *reinterpret_cast<float4 *>(row + 8 + 4 * lane) = u8x4_to_float4(u);
+        __syncwarp();
+        float a[20];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const float4 t4 = *reinterpret_cast<const float4 *>(row + 4 * lane + 4 * q);
+            a[4 * q] = t4.x; a[4 * q + 1] = t4.y; a[4 * q + 2] = t4.z; a[4 * q + 3] = t4.w;
+        }
+        // blurred values of the output row (written 5 steps ago by this very lane)
+        const float4 bf = *reinterpret_cast<const float4 *>(ring + ((s + 3) & (GD_RING - 1)) * GD_ROWF + 8 + 4 * lane);
+        float r[4], m[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) r[k] = gauss_row<TAIL>(&a[3 + k], row_tail);
+        switch (j) {
+            case 0: gd_window<0, TAIL>(win, r, m, col_tail); break;
+            case 1: gd_window<1, TAIL>(win, r, m, col_tail); break;
+            case 2: gd_window<2, TAIL>(win, r, m, col_tail); break;
+            case 3: gd_window<3, TAIL>(win, r, m, col_tail); break;
+            case 4: gd_window<4, TAIL>(win, r, m, col_tail); break;
+            case 5: gd_window<5, TAIL>(win, r, m, col_tail); break;
+            case 6: gd_window<6, TAIL>(win, r, m, col_tail); break;
+            case 7: gd_window<7, TAIL>(win, r, m, col_tail); break;
+            case 8: gd_window<8, TAIL>(win, r, m, col_tail); break;
+            case 9: gd_window<9, TAIL>(win, r, m, col_tail); break;
+            default: gd_window<10, TAIL>(win, r, m, col_tail); break;
+        }
+        const uint32_t bits = gd_decide(m, bf, c_mask, c_mark);
+        if (s >= 10) *dst = (uint8_t)bits;
+        dst += dec_pitch;
+        j = j == 10 ? 0 : j + 1;
+    }
+}
+
+// mean/std mode (track_eval.py:248-253, cv2.threshold on the blurred image): decision byte = (b > T) per pixel, no Gaussian.
+__global__ void __launch_bounds__(256) scalar_decide_kernel(FrontParams p)
+{
+    const int nb = p.dec_pitch;                   // bytes per decision row (= 4-pixel groups)
+    const int64_t total = (int64_t)p.n_frames * p.h * nb;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int g = (int)(i % nb);
+        const int64_t fr = i / nb;
+        const int y = (int)(fr % p.h), f = (int)(fr / p.h);
+        const int thr = p.scalar_thr[f];
+        const uint32_t u = *reinterpret_cast<const uint32_t *>(p.plane + (int64_t)f * p.plane_stride + (int64_t)(y + 5) * p.pitch + 8 + 4 * g);
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) bits |= ((int)((u >> (8 * k)) & 0xFFu) > thr) ? (1u << k) : 0u;
+        p.decisions[(int64_t)f * p.dec_stride + (int64_t)y * nb + g] = (uint8_t)bits;
+    }
+}
+
+// ---- K1c: decision bytes -> bit masks ---------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t squeeze_nibbles(uint32_t v)   // nibbles at bits 0-3, 8-11, 16-19, 24-27 -> low 16 bits
+{
+    v = (v | (v >> 4)) & 0x00FF00FFu;
+    return (v | (v >> 8)) & 0x0000FFFFu;
+}
+
+__global__ void __launch_bounds__(256) pack_masks_kernel(FrontParams p)
+{
+    const int ww = p.ww;
+    const int64_t total = (int64_t)p.n_frames * p.h * ww;
+    const uint32_t inv = p.inverted ? 0xFFFFFFFFu : 0u;
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int word = (int)(i % ww);
+        const int64_t fr = i / ww;
+        const int y = (int)(fr % p.h), f = (int)(fr / p.h);
+        const uint2 d = *reinterpret_cast<const uint2 *>(p.decisions + (int64_t)f * p.dec_stride + (int64_t)y * p.dec_pitch + 8 * word);
+        const uint32_t mask = squeeze_nibbles(d.x & 0x0F0F0F0Fu) | (squeeze_nibbles(d.y & 0x0F0F0F0Fu) << 16);
+        const uint32_t mark = squeeze_nibbles((d.x >> 4) & 0x0F0F0F0Fu) | (squeeze_nibbles((d.y >> 4) & 0x0F0F0F0Fu) << 16);
+        const int left = p.w - 32 * word;
+        const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+        p.mask_bits[i] = (mask ^ inv) & valid;
+        if (p.marker_bits) p.marker_bits[i] = (mark ^ inv) & valid;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------------------
 // BGR -> grey pre-pass (cv2.cvtColor, track_eval.py:180).  Streaming kernel: 8 pixels (24 bytes in, 8 bytes out) per
 // thread with 64-bit accesses.  Used in front of the strip kernel for 3-channel input: doing the luma inside the strip
 // kernel costs more than this pass (strided 12-byte loads per lane, luma repeated in the halo pass, register pressure).
 // ---------------------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint32_t luma_dp(uint32_t px)        // px = B | G << 8 | R << 16 (byte 3 ignored)
-{
-    constexpr uint32_t HI = 14u | (75u << 8) | (38u << 16), LO = 151u | (35u << 8) | (70u << 16);
-    return (__dp4a(px, HI, 0u) * 256u + __dp4a(px, LO, 16384u)) >> 15;
-}
 
 __global__ void __launch_bounds__(256) bgr_to_grey_kernel(const uint8_t *frames, int64_t frame_stride, uint8_t *grey, int64_t px_per_frame,
                                                           int n_frames, int vec_ok)
@@ -671,6 +1032,80 @@ cudaError_t launch_frontend_strip(const FrontParams &p, cudaStream_t st)
     const unsigned grid = (unsigned)((tasks + STRIP_WARPS - 1) / STRIP_WARPS);
     if (p.channels == 3) frontend_strip_kernel<3><<<grid, STRIP_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
     else frontend_strip_kernel<1><<<grid, STRIP_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_frontend_v3(const FrontParams &p, cudaStream_t st, int *n_launched)
+{
+    int launched = 2;                                 // K1a + margins
+    // K1a
+    {
+        const int n_strips = (p.w + PB_COLS - 1) / PB_COLS;
+        const int n_chunks = (p.h + 47) / 48;
+        const int rows_per_chunk = (p.h + n_chunks - 1) / n_chunks;
+        const int64_t tasks = (int64_t)n_strips * n_chunks * p.n_frames;
+        const unsigned grid = (unsigned)((tasks + PB_WARPS - 1) / PB_WARPS);
+        const bool fast = (p.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.frames) & 3) == 0) && (p.frame_stride % 4 == 0);
+        if (p.channels == 3) {
+            if (fast) blur_prepass_kernel<3, true><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
+            else blur_prepass_kernel<3, false><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
+        } else {
+            if (fast) blur_prepass_kernel<1, true><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
+            else blur_prepass_kernel<1, false><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
+        }
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+        plane_margins_kernel<<<148 * 4, 256, 0, st>>>(p);
+        e = cudaGetLastError();
+        if (e != cudaSuccess) return e;
+    }
+    // K1b
+    if (p.scalar_thr) {
+        scalar_decide_kernel<<<148 * 8, 256, 0, st>>>(p);
+        ++launched;
+    } else {
+        const int n_strips = (p.w + 127) / 128;
+        // strips from this one on contain scalar-tail columns (none if w % 8 == 0)
+        const int first_tail = p.col_tail_from < p.w ? p.col_tail_from / 128 : n_strips;
+        // row chunks: every chunk recomputes 10 halo rows, every wave of CTAs costs (rows + 10) steps -> pick the chunk count
+        // that minimises waves * (rows + 10) for this batch
+        static int ctas_per_sm = 0;
+        if (!ctas_per_sm) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, gauss_decide_kernel<false>, GD_WARPS * 32, 0);
+            if (ctas_per_sm < 1) ctas_per_sm = 1;
+        }
+        int sms = 148, dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const double slots = (double)sms * ctas_per_sm;
+        auto launch = [&](int first_strip, int ns, bool tail) -> cudaError_t {
+            if (ns <= 0) return cudaSuccess;
+            ++launched;
+            int best_chunks = 1; double best_cost = 1e300;
+            for (int nc = 1; nc <= 32 && nc * 16 <= p.h; ++nc) {
+                const int rows = (p.h + nc - 1) / nc;
+                const double ctas = (double)((int64_t)ns * nc * p.n_frames + GD_WARPS - 1) / GD_WARPS;
+                const double waves = ctas / slots;
+                const double cost = (waves < 1.0 ? 1.0 : (waves + 0.35)) * (rows + 10);  // +0.35: expected tail of a partial wave
+                if (cost < best_cost) { best_cost = cost; best_chunks = nc; }
+            }
+            const int n_chunks = best_chunks;
+            const int rows_per_chunk = (p.h + n_chunks - 1) / n_chunks;
+            const int64_t tasks = (int64_t)ns * n_chunks * p.n_frames;
+            const unsigned grid = (unsigned)((tasks + GD_WARPS - 1) / GD_WARPS);
+            if (tail) gauss_decide_kernel<true><<<grid, GD_WARPS * 32, 0, st>>>(p, first_strip, ns, n_chunks, rows_per_chunk);
+            else gauss_decide_kernel<false><<<grid, GD_WARPS * 32, 0, st>>>(p, first_strip, ns, n_chunks, rows_per_chunk);
+            return cudaGetLastError();
+        };
+        cudaError_t e1 = launch(0, first_tail, false);
+        if (e1 != cudaSuccess) return e1;
+        e1 = launch(first_tail, n_strips - first_tail, true);
+        if (e1 != cudaSuccess) return e1;
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    pack_masks_kernel<<<148 * 8, 256, 0, st>>>(p);
+    if (n_launched) *n_launched = launched + 1;
     return cudaGetLastError();
 }
 

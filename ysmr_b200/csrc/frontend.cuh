@@ -17,12 +17,20 @@ struct FrontParams {
     float k[11];                 // cv2.getGaussianKernel(11, 0, CV_32F)
     int row_tail_from;           // w - w % 4 : first column of OpenCV's scalar tail of the row filter
     int col_tail_from;           // w - w % 8 : first column of the scalar tail of the column filter
+    // generation-3 front-end intermediates (owned by the context)
+    uint8_t *plane;              // blurred planes: [n_frames] x plane_stride bytes, (h + 10) rows of `pitch` bytes
+    int64_t plane_stride;
+    int pitch;                   // 16 + round_up(w, 128)
+    uint8_t *decisions;          // decision bytes: [n_frames] x dec_stride bytes, h rows of dec_pitch bytes
+    int64_t dec_stride;
+    int dec_pitch;               // 32 * ceil(w / 128)
     // optional byte-image dumps [n_frames][h][w] (tile kernel only)
     uint8_t *dbg_grey, *dbg_blurred, *dbg_mean;
 };
 
 cudaError_t launch_frontend_tile(const FrontParams &p, cudaStream_t st);
 cudaError_t launch_frontend_strip(const FrontParams &p, cudaStream_t st);
+cudaError_t launch_frontend_v3(const FrontParams &p, cudaStream_t st, int *n_launched);
 cudaError_t launch_bgr_to_grey(const uint8_t *frames, int64_t frame_stride, uint8_t *grey, int h, int w, int n_frames, cudaStream_t st);
 cudaError_t launch_unpack_bits(const uint32_t *bits, uint8_t *bytes, int64_t rows, int w, int ww, cudaStream_t st);
 cudaError_t launch_frame_moments(const uint8_t *frames, int64_t stride, int n_frames, int h, int w, int channels,
