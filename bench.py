@@ -38,7 +38,7 @@ def parse():
     ap.add_argument('--frames', type=int, default=9000, help='frames per GPU (configs[1]: 9000)')
     ap.add_argument('--channels', type=int, default=3, choices=[1, 3])
     ap.add_argument('--cells', type=int, default=50)
-    ap.add_argument('--batch', type=int, default=256, help='frames per detect launch')
+    ap.add_argument('--batch', type=int, default=592, help='frames per detect launch')
     ap.add_argument('--cpu-frames', type=int, default=300, help='frames of the bounded CPU sample')
     ap.add_argument('--e2e-frames', type=int, default=1000, help='frames in the pinned host buffer of the e2e leg')
     ap.add_argument('--no-e2e', action='store_true')

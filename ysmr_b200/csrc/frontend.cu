@@ -561,42 +561,65 @@ __device__ __forceinline__ void luma4(uint32_t w0, uint32_t w1, uint32_t w2, uin
     pb = luma_b23_0(w1, w2) | (luma_b123(w2) << 16);
 }
 
-// One row of a lane.  FAST: w % 4 == 0 and 4-byte aligned frames, so every lane inside the image loads whole 32-bit words and
-// REFLECT_101 at the left / right image border is done in registers; otherwise per-pixel loads (any width, slow).
-template <int C, bool FAST>
-__device__ __forceinline__ GreyRow load_row(const uint8_t *frame, int w, int y, int gx, int nvalid)
+// Per-lane constants of the FAST path (w % 4 == 0, 4-byte aligned frames): every load is a whole 32-bit word at an address
+// that is always inside the row (lanes at the image border re-load one of their own words and the REFLECT_101 value is
+// then taken from registers), so the row loop has no divergent branches.
+struct LaneGeom {
+    int hi_off;        // word offset of pixels 4..7 (0 when the lane only has 4 valid pixels: w % 8 == 4, last lane)
+    int l_off, r_off;  // word offsets of the words holding pixel gx-1 / gx+8 (0 at the image border)
+    bool half, left_edge, right_edge;
+};
+
+template <int C>
+__device__ __forceinline__ LaneGeom lane_geom(int w, int gx)
+{
+    LaneGeom g;
+    g.half = w - gx < 8;
+    g.left_edge = gx == 0;
+    g.right_edge = !g.half && gx + 8 >= w;
+    g.hi_off = g.half ? 0 : C;
+    g.l_off = g.left_edge ? 0 : -1;
+    g.r_off = (g.half || g.right_edge) ? 0 : 2 * C;
+    return g;
+}
+
+template <int C>
+__device__ __forceinline__ GreyRow load_row_fast(const uint8_t *rowp, const LaneGeom &lg)
+{
+    const uint32_t *q = reinterpret_cast<const uint32_t *>(rowp);
+    GreyRow g;
+    uint32_t l, r;
+    if (C == 1) {
+        const uint32_t lo = __ldg(q), hi = __ldg(q + lg.hi_off);
+        l = __ldg(q + lg.l_off) >> 24; r = __ldg(q + lg.r_off) & 0xFFu;
+        g.p01 = __byte_perm(lo, 0, 0x4140); g.p23 = __byte_perm(lo, 0, 0x4342);
+        g.p45 = __byte_perm(hi, 0, 0x4140); g.p67 = __byte_perm(hi, 0, 0x4342);
+    } else {
+        const uint32_t *qh = q + 3 * lg.hi_off / C;        // hi_off is 0 or C -> 0 or 3 words
+        const uint32_t a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
+        const uint32_t b0 = __ldg(qh), b1 = __ldg(qh + 1), b2 = __ldg(qh + 2);
+        const uint32_t vl = __ldg(q + lg.l_off), vr = __ldg(q + 3 * lg.r_off / C);
+        luma4(a0, a1, a2, g.p01, g.p23);
+        luma4(b0, b1, b2, g.p45, g.p67);
+        l = luma_b123(vl); r = luma_b012(vr);
+    }
+    if (lg.left_edge) l = g.p01 >> 16;                     // REFLECT_101: column -1 is column 1
+    if (lg.right_edge) r = g.p67 & 0xFFFFu;                // column w is column w-2 (w % 8 == 0)
+    if (lg.half) { g.p45 = g.p23 & 0xFFFFu; g.p67 = 0; }  // column w is column w-2 (w % 8 == 4)
+    g.side = l | (r << 16);
+    return g;
+}
+
+// generic path: per-pixel loads with REFLECT_101 (any width / alignment, slow)
+template <int C>
+__device__ __forceinline__ GreyRow load_row_generic(const uint8_t *frame, int w, int y, int gx)
 {
     GreyRow g;
-    if (FAST) {
-        const uint32_t *q = reinterpret_cast<const uint32_t *>(frame + ((int64_t)y * w + gx) * C);
-        g.p45 = 0; g.p67 = 0;
-        uint32_t l = 0, r = 0;
-        if (C == 1) {
-            const uint32_t lo = __ldg(q);
-            g.p01 = __byte_perm(lo, 0, 0x4140); g.p23 = __byte_perm(lo, 0, 0x4342);
-            if (nvalid >= 8) {
-                const uint32_t hi = __ldg(q + 1);
-                g.p45 = __byte_perm(hi, 0, 0x4140); g.p67 = __byte_perm(hi, 0, 0x4342);
-            }
-            if (gx != 0) l = __ldg(q - 1) >> 24;
-            if (nvalid >= 8 && gx + 8 < w) r = __ldg(q + 2) & 0xFFu;
-        } else {
-            luma4(__ldg(q), __ldg(q + 1), __ldg(q + 2), g.p01, g.p23);
-            if (nvalid >= 8) luma4(__ldg(q + 3), __ldg(q + 4), __ldg(q + 5), g.p45, g.p67);
-            if (gx != 0) l = luma_b123(__ldg(q - 1));
-            if (nvalid >= 8 && gx + 8 < w) r = luma_b012(__ldg(q + 6));
-        }
-        if (gx == 0) l = g.p01 >> 16;                              // REFLECT_101: column -1 is column 1
-        if (nvalid < 8) g.p45 = g.p23 & 0xFFFFu;                   // column w is column w-2 (w % 8 == 4)
-        else if (gx + 8 >= w) r = g.p67 & 0xFFFFu;                 // column w is column w-2 (w % 8 == 0)
-        g.side = l | (r << 16);
-    } else {
-        uint32_t v[10];
+    uint32_t v[10];
 #pragma unroll
-        for (int k = 0; k < 10; ++k) v[k] = grey_px<C>(frame, w, y, reflect101(gx - 1 + k, w));
-        g.p01 = v[1] | (v[2] << 16); g.p23 = v[3] | (v[4] << 16); g.p45 = v[5] | (v[6] << 16); g.p67 = v[7] | (v[8] << 16);
-        g.side = v[0] | (v[9] << 16);
-    }
+    for (int k = 0; k < 10; ++k) v[k] = grey_px<C>(frame, w, y, reflect101(gx - 1 + k, w));
+    g.p01 = v[1] | (v[2] << 16); g.p23 = v[3] | (v[4] << 16); g.p45 = v[5] | (v[6] << 16); g.p67 = v[7] | (v[8] << 16);
+    g.side = v[0] | (v[9] << 16);
     return g;
 }
 
@@ -605,6 +628,20 @@ __device__ __forceinline__ GreyRow add_rows(const GreyRow &a, const GreyRow &b)
     GreyRow s;
     s.p01 = a.p01 + b.p01; s.p23 = a.p23 + b.p23; s.p45 = a.p45 + b.p45; s.p67 = a.p67 + b.p67; s.side = a.side + b.side;
     return s;
+}
+
+__device__ __forceinline__ uint2 blur_row(const GreyRow &v)
+{
+    const uint32_t m0 = __byte_perm(v.side, v.p01, 0x5410);   // (v[-1], v0)
+    const uint32_t m1 = __byte_perm(v.p01, v.p23, 0x5432);    // (v1, v2)
+    const uint32_t m2 = __byte_perm(v.p23, v.p45, 0x5432);    // (v3, v4)
+    const uint32_t m3 = __byte_perm(v.p45, v.p67, 0x5432);    // (v5, v6)
+    const uint32_t m4 = __byte_perm(v.p67, v.side, 0x7632);   // (v7, v8)
+    const uint32_t o01 = (m0 + m1 + 0x00080008u + 2 * v.p01) >> 4;
+    const uint32_t o23 = (m1 + m2 + 0x00080008u + 2 * v.p23) >> 4;
+    const uint32_t o45 = (m2 + m3 + 0x00080008u + 2 * v.p45) >> 4;
+    const uint32_t o67 = (m3 + m4 + 0x00080008u + 2 * v.p67) >> 4;
+    return make_uint2(__byte_perm(o01, o23, 0x6420), __byte_perm(o45, o67, 0x6420));
 }
 
 template <int C, bool FAST>
@@ -622,33 +659,27 @@ __global__ void __launch_bounds__(PB_WARPS * 32) blur_prepass_kernel(FrontParams
     const uint8_t *frame = p.frames + (int64_t)f * p.frame_stride;
     const int gx = strip * PB_COLS + 8 * lane;
     if (gx >= w) return;                                          // no cross-lane traffic in this kernel
-    const int nvalid = FAST ? (w - gx >= 8 ? 8 : 4) : 8;
     uint8_t *dst = p.plane + (int64_t)f * p.plane_stride + (int64_t)(y0 + 5) * p.pitch + 8 + gx;
     const int pitch = p.pitch;
-
-    GreyRow a = load_row<C, FAST>(frame, w, reflect101(y0 - 1, h), gx, nvalid);
-    GreyRow b = load_row<C, FAST>(frame, w, y0, gx, nvalid);
-    GreyRow s_prev = add_rows(a, b);                              // S(y-1) = g(y-1) + g(y)
-    GreyRow nxt = load_row<C, FAST>(frame, w, reflect101(y0 + 1, h), gx, nvalid);
+    const int64_t stride = (int64_t)w * C;
+    const uint8_t *col = frame + (int64_t)gx * C;                 // this lane's column in row 0
+    const LaneGeom lg = lane_geom<C>(w, gx);
+    auto row = [&](int y) -> GreyRow {                            // y already reflected into [0, h)
+        if (FAST) return load_row_fast<C>(col + y * stride, lg);
+        return load_row_generic<C>(frame, w, y, gx);
+    };
+    // rows y-1, y, y+1 slide through registers as S(y-1) = g(y-1) + g(y) and g(y); the row after next is in flight
+    GreyRow b = row(y0);
+    GreyRow s_prev = add_rows(row(reflect101(y0 - 1, h)), b);
+    GreyRow nxt = row(reflect101(y0 + 1, h));
+#pragma unroll 2
     for (int y = y0; y < y1; ++y) {
         const GreyRow c = nxt;
-        if (y + 1 < y1) nxt = load_row<C, FAST>(frame, w, reflect101(y + 2, h), gx, nvalid);     // prefetch
+        int yn = y + 2; yn = yn >= h ? 2 * h - 2 - yn : yn;       // REFLECT_101 below the image (last chunk only)
+        if (y + 1 < y1) nxt = row(yn);                            // prefetch
         const GreyRow s_cur = add_rows(b, c);                     // S(y) = g(y) + g(y+1)
-        const GreyRow v = add_rows(s_prev, s_cur);                // vertical 1-2-1
+        *reinterpret_cast<uint2 *>(dst) = blur_row(add_rows(s_prev, s_cur));      // vertical 1-2-1, then horizontal
         s_prev = s_cur; b = c;
-        const uint32_t m0 = __byte_perm(v.side, v.p01, 0x5410);   // (v[-1], v0)
-        const uint32_t m1 = __byte_perm(v.p01, v.p23, 0x5432);    // (v1, v2)
-        const uint32_t m2 = __byte_perm(v.p23, v.p45, 0x5432);    // (v3, v4)
-        const uint32_t m3 = __byte_perm(v.p45, v.p67, 0x5432);    // (v5, v6)
-        const uint32_t m4 = __byte_perm(v.p67, v.side, 0x7632);   // (v7, v8)
-        const uint32_t o01 = (m0 + m1 + 0x00080008u + 2 * v.p01) >> 4;
-        const uint32_t o23 = (m1 + m2 + 0x00080008u + 2 * v.p23) >> 4;
-        const uint32_t o45 = (m2 + m3 + 0x00080008u + 2 * v.p45) >> 4;
-        const uint32_t o67 = (m3 + m4 + 0x00080008u + 2 * v.p67) >> 4;
-        uint2 out;
-        out.x = __byte_perm(o01, o23, 0x6420);
-        out.y = __byte_perm(o45, o67, 0x6420);
-        *reinterpret_cast<uint2 *>(dst) = out;
         dst += pitch;
     }
 }
@@ -711,12 +742,11 @@ __device__ __forceinline__ float sub_sat(float a, float b)
 
 __device__ __forceinline__ float4 u8x4_to_float4(uint32_t u)
 {
-    float4 f;
-    f.x = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7540)) - 8388608.0f;
-    f.y = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7541)) - 8388608.0f;
-    f.z = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7542)) - 8388608.0f;
-    f.w = __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7543)) - 8388608.0f;
-    return f;
+    // 0x4B000000 | byte is the float 2^23 + byte
+    const float2 neg = make_float2(-8388608.0f, -8388608.0f);
+    const float2 a = fadd2(make_float2(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7540)), __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7541))), neg);
+    const float2 b = fadd2(make_float2(__uint_as_float(__byte_perm(u, 0x4B000000u, 0x7542)), __uint_as_float(__byte_perm(u, 0x4B000000u, 0x7543))), neg);
+    return make_float4(a.x, a.y, b.x, b.y);
 }
 
 // One step of the register window: file this step's row-pass results in slot J and run the column pass centred 5 steps
@@ -737,20 +767,31 @@ __device__ __forceinline__ void gd_window(float2 (&win)[11][2], const float (&r)
     }
 }
 
-// lane's decision byte from the four float means and the four blurred values of the output row
+// lane's decision byte from the four float means and the four blurred values of the output row.  Packed where the operation
+// exists in packed form (FADD2 / FFMA2 halve the issue slots; sub.sat has no packed form):
+//     R = mean + 1.5*2^23 ; e = b - R (exact: integers below 2^24) ; d = sat(e + (1.5*2^23 - t)) ; byte = sum d_k 2^k
 __device__ __forceinline__ uint32_t gd_decide(const float (&m)[4], const float4 bf, float c_mask, float c_mark)
 {
-    const float b[4] = {bf.x, bf.y, bf.z, bf.w};
-    float acc = 8388608.0f;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) {
-        const float r = __fadd_rn(m[k], GD_MAGIC);
-        const float d_mask = sub_sat(__fadd_rn(b[k], c_mask), r);
-        const float d_mark = sub_sat(__fadd_rn(b[k], c_mark), r);
-        acc = __fmaf_rn(d_mask, (float)(1 << k), acc);
-        acc = __fmaf_rn(d_mark, (float)(16 << k), acc);
-    }
-    return __float_as_uint(acc);
+    // two steps on purpose: R rounds the mean to an integer first, then the difference is exact
+    const float2 r01 = fadd2(make_float2(m[0], m[1]), make_float2(GD_MAGIC, GD_MAGIC));
+    const float2 r23 = fadd2(make_float2(m[2], m[3]), make_float2(GD_MAGIC, GD_MAGIC));
+    const float2 e01 = fadd2(make_float2(bf.x, bf.y), make_float2(-r01.x, -r01.y));
+    const float2 e23 = fadd2(make_float2(bf.z, bf.w), make_float2(-r23.x, -r23.y));
+    float2 da01, da23, db01, db23;
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(da01.x) : "f"(e01.x), "f"(c_mask));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(da01.y) : "f"(e01.y), "f"(c_mask));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(da23.x) : "f"(e23.x), "f"(c_mask));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(da23.y) : "f"(e23.y), "f"(c_mask));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(db01.x) : "f"(e01.x), "f"(c_mark));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(db01.y) : "f"(e01.y), "f"(c_mark));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(db23.x) : "f"(e23.x), "f"(c_mark));
+    asm("add.sat.f32 %0, %1, %2;" : "=f"(db23.y) : "f"(e23.y), "f"(c_mark));
+    // even pixels accumulate in .x, odd pixels in .y with the same (broadcast) weights; byte = x + 2 y on top of 2^23
+    float2 acc = fadd2(da01, make_float2(8388608.0f, 0.0f));
+    acc = ffma2(da23, make_float2(4.f, 4.f), acc);
+    acc = ffma2(db01, make_float2(16.f, 16.f), acc);
+    acc = ffma2(db23, make_float2(64.f, 64.f), acc);
+    return __float_as_uint(__fmaf_rn(acc.y, 2.0f, acc.x));
 }
 
 // TAIL = false: strips without scalar-tail columns (every column fused).  TAIL = true: the strip(s) that contain OpenCV's
@@ -866,21 +907,20 @@ __device__ __forceinline__ uint32_t squeeze_nibbles(uint32_t v)   // nibbles at 
 
 __global__ void __launch_bounds__(256) pack_masks_kernel(FrontParams p)
 {
-    const int ww = p.ww;
-    const int64_t total = (int64_t)p.n_frames * p.h * ww;
+    // grid = (words of a frame / 256, frames): 32-bit index arithmetic only
+    const int ww = p.ww, f = blockIdx.y;
+    const uint32_t i = blockIdx.x * 256u + threadIdx.x;
+    if (i >= (uint32_t)(p.h * ww)) return;
+    const uint32_t y = i / (uint32_t)ww, word = i - y * (uint32_t)ww;
     const uint32_t inv = p.inverted ? 0xFFFFFFFFu : 0u;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int word = (int)(i % ww);
-        const int64_t fr = i / ww;
-        const int y = (int)(fr % p.h), f = (int)(fr / p.h);
-        const uint2 d = *reinterpret_cast<const uint2 *>(p.decisions + (int64_t)f * p.dec_stride + (int64_t)y * p.dec_pitch + 8 * word);
-        const uint32_t mask = squeeze_nibbles(d.x & 0x0F0F0F0Fu) | (squeeze_nibbles(d.y & 0x0F0F0F0Fu) << 16);
-        const uint32_t mark = squeeze_nibbles((d.x >> 4) & 0x0F0F0F0Fu) | (squeeze_nibbles((d.y >> 4) & 0x0F0F0F0Fu) << 16);
-        const int left = p.w - 32 * word;
-        const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
-        p.mask_bits[i] = (mask ^ inv) & valid;
-        if (p.marker_bits) p.marker_bits[i] = (mark ^ inv) & valid;
-    }
+    const uint2 d = *reinterpret_cast<const uint2 *>(p.decisions + (int64_t)f * p.dec_stride + (int64_t)y * p.dec_pitch + 8 * word);
+    const uint32_t mask = squeeze_nibbles(d.x & 0x0F0F0F0Fu) | (squeeze_nibbles(d.y & 0x0F0F0F0Fu) << 16);
+    const uint32_t mark = squeeze_nibbles((d.x >> 4) & 0x0F0F0F0Fu) | (squeeze_nibbles((d.y >> 4) & 0x0F0F0F0Fu) << 16);
+    const int left = p.w - 32 * (int)word;
+    const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+    const int64_t o = (int64_t)f * p.h * ww + i;
+    p.mask_bits[o] = (mask ^ inv) & valid;
+    if (p.marker_bits) p.marker_bits[o] = (mark ^ inv) & valid;
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -1104,7 +1144,7 @@ cudaError_t launch_frontend_v3(const FrontParams &p, cudaStream_t st, int *n_lau
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
-    pack_masks_kernel<<<148 * 8, 256, 0, st>>>(p);
+    pack_masks_kernel<<<dim3((unsigned)((p.h * p.ww + 255) / 256), (unsigned)p.n_frames), 256, 0, st>>>(p);
     if (n_launched) *n_launched = launched + 1;
     return cudaGetLastError();
 }

@@ -5,6 +5,10 @@
 
 namespace ysmr {
 
+#ifndef LABEL_MIN_CTAS
+#define LABEL_MIN_CTAS 4
+#endif
+
 // ---- CTA policy for label_frame ------------------------------------------------------------------------------------
 struct DevCta {
     uint32_t *warp_sums;   // shared, [33]
@@ -54,7 +58,7 @@ struct DevCta {
 };
 
 // One CTA per frame slot; CTAs stride over the frames of the batch and reuse their private scratch.
-__global__ void __launch_bounds__(LABEL_THREADS) label_kernel(LabelLaunch L)
+__global__ void __launch_bounds__(LABEL_THREADS, LABEL_MIN_CTAS) label_kernel(LabelLaunch L)
 {
     __shared__ uint32_t warp_sums[33];
     DevCta cta{warp_sums};
