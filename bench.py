@@ -39,7 +39,7 @@ def parse():
     ap.add_argument('--channels', type=int, default=3, choices=[1, 3])
     ap.add_argument('--cells', type=int, default=50)
     ap.add_argument('--batch', type=int, default=592, help='frames per detect launch')
-    ap.add_argument('--cpu-frames', type=int, default=300, help='frames of the bounded CPU sample')
+    ap.add_argument('--cpu-frames', type=int, default=900, help='frames of the bounded CPU sample (about 15 s)')
     ap.add_argument('--e2e-frames', type=int, default=1000, help='frames in the pinned host buffer of the e2e leg')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
@@ -189,7 +189,7 @@ def main():
         render_frames_torch(scene, rank * F + a, rank * F + b, dev, channels=Cn, out=frames[a:b])
     torch.cuda.synchronize()
 
-    MB, MT = 512, 1024
+    MB, MT = 128, 1024              # capacities: detections per frame (the scene has ~50), live tracks
     ctx = Context(H, W, Cn, local, max_batch=args.batch, max_blobs=MB, max_tracks=MT)
     rows_cap = world * F * 160
     rows_buf = torch.empty(rows_cap * ROW_DTYPE.itemsize, dtype=torch.uint8, device=dev) if rank == 0 else None
@@ -198,42 +198,44 @@ def main():
         ctx.reset()
         return ctx.track_device(frames, 0, rows_capacity=rows_cap, rows_buf=rows_buf, return_device=True)
 
-    # multi-GPU: every rank detects its frame range; detection records are gathered over NCCL to rank 0, which runs the one
-    # sequential linker over all ranges in frame order (ysmr_b200/shard.py)
-    from ysmr_b200.shard import track_sharded
-    state = {}
+    # multi-GPU: every rank detects its own frame range; rank 0 runs the whole pipeline on its range (linker
+    # overlapped with detection), the other ranks' detection records (count + 5 floats per blob) are gathered over NCCL, and
+    # rank 0's one sequential linker continues through them in frame order.  Linking cannot be sharded exactly.
+    import ctypes as C
 
-    def detect_range(a, b):                      # global frame indices; this rank holds [rank*F, (rank+1)*F)
-        lo = a - rank * F
-        counts = torch.empty(b - a, dtype=torch.int32, device=dev)
-        blobs = torch.empty((b - a, MB, 5), dtype=torch.float32, device=dev)
-        for i in range(0, b - a, args.batch):
-            j = min(b - a, i + args.batch)
-            c, bl = ctx.detect(frames[lo + i:lo + j], a + i)
+    def detect_all():
+        counts = torch.empty(F, dtype=torch.int32, device=dev)
+        blobs = torch.empty((F, MB, 5), dtype=torch.float32, device=dev)
+        for i in range(0, F, args.batch):
+            j = min(F, i + args.batch)
+            c, bl = ctx.detect(frames[i:j], rank * F + i)
             counts[i:j] = c; blobs[i:j] = bl
         return counts, blobs
 
-    def link_range(c, b, first):
-        import ctypes as C
-        if 'lctx' not in state or state['width'] != b.shape[1]:
-            state['lctx'] = Context(H, W, Cn, local, max_batch=8, max_blobs=int(b.shape[1]), max_tracks=MT)
-            state['width'] = int(b.shape[1])
-        l = state['lctx']
-        if first == 0:
-            l.reset(); state['total'] = 0
-        nr = torch.zeros(1, dtype=torch.int64, device=dev)
-        off = state['total'] * ROW_DTYPE.itemsize
-        l._check(l.lib.ysmr_link(l._h, C.c_void_p(c.data_ptr()), C.c_void_p(b.data_ptr()), int(first), int(c.numel()),
-                                 C.c_void_p(rows_buf.data_ptr() + off), rows_cap - state['total'],
-                                 C.c_void_p(nr.data_ptr()), l._stream_ptr()))
-        state['total'] += int(nr.item())
-        return None
-
     def step_multi():
-        track_sharded(world * F, world, rank, detect_range, link_range, 0, dist, dev)
         if rank == 0:
-            return rows_buf, torch.tensor([state['total']], dtype=torch.int64, device=dev)
-        return None, None
+            ctx.reset()
+            _, n0 = ctx.track_device(frames, 0, rows_capacity=rows_cap, rows_buf=rows_buf, return_device=True)
+            counts = torch.zeros(F, dtype=torch.int32, device=dev)
+            blobs = torch.zeros((F, MB, 5), dtype=torch.float32, device=dev)
+            cs = [torch.empty_like(counts) for _ in range(world)]
+            bs = [torch.empty_like(blobs) for _ in range(world)]
+        else:
+            counts, blobs = detect_all()
+            cs = bs = None
+        dist.gather(counts, cs, dst=0)
+        dist.gather(blobs, bs, dst=0)
+        if rank != 0:
+            return None, None
+        total = n0.clone()
+        nr = torch.zeros(1, dtype=torch.int64, device=dev)
+        for r in range(1, world):
+            off = int(total.item()) * ROW_DTYPE.itemsize
+            ctx._check(ctx.lib.ysmr_link(ctx._h, C.c_void_p(cs[r].data_ptr()), C.c_void_p(bs[r].data_ptr()), r * F, F,
+                                         C.c_void_p(rows_buf.data_ptr() + off), rows_cap - int(total.item()),
+                                         C.c_void_p(nr.data_ptr()), ctx._stream_ptr()))
+            total += nr
+        return rows_buf, total
 
     step = step_single if world == 1 else step_multi
 
@@ -262,8 +264,6 @@ def main():
     prof = ctx.get_profile()
     ctx.set_profiling(False)
     launches = ctx.launch_count() - launches0
-    if world > 1 and rank == 0 and 'lctx' in state:
-        launches += state['lctx'].launch_count()
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -280,15 +280,30 @@ def main():
     rows = rows_dev[:n_rows * ROW_DTYPE.itemsize].cpu().numpy().view(ROW_DTYPE)
     n_tracks = int(rows['track_id'].max()) + 1 if n_rows else 0
 
-    # ---- roofline of the dominant kernel (front-end): algorithmic bytes = H*W*C per frame, frames/launch ----
+    # ---- roofline: algorithmic bytes = H*W*C per frame (input read once), against the front-end launches that
+    # consume them (K1a blur pre-pass, K1b Gaussian + decisions -- the dominant kernel --, K1c mask packing), timed with
+    # CUDA events on the detection stream inside the timed region.  Per-kernel own DRAM traffic comes from the committed
+    # ncu capture (profiles/r1_traffic.json) when present.
     fe_ms, fe_n = prof['frontend']
     bytes_per_frame = H * W * Cn
     frames_per_launch = (F * args.steps) / max(fe_n, 1)
-    achieved = (bytes_per_frame * frames_per_launch) / (fe_ms / max(fe_n, 1) / 1000.0) / 1e9 if fe_ms > 0 else 0.0
-    roofline = {'bound': 'hbm', 'kernel': 'frontend (K1)', 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s',
-                'frac': achieved / hbm_peak, 'traffic': None, 'peak_source': peak_src,
-                'algorithmic_bytes_per_frame': bytes_per_frame, 'frames_per_launch': frames_per_launch,
-                'avg_launch_ms': fe_ms / max(fe_n, 1),
+    per_launch_ms = fe_ms / max(fe_n, 1)
+    achieved = (bytes_per_frame * frames_per_launch) / (per_launch_ms / 1000.0) / 1e9 if fe_ms > 0 else 0.0
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
+        traffic = float(tj['frontend_dram_bytes_per_frame']) * frames_per_launch
+    except Exception:
+        pass
+    kb = prof['k1b']
+    k1b_ms = kb[0] / max(kb[1], 1)
+    roofline = {'bound': 'hbm', 'kernel': 'front-end launches of one batch: K1a blur_prepass + margins, K1b gauss_decide (dominant), K1c pack_masks',
+                'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
+                'peak_source': peak_src, 'algorithmic_bytes_per_frame': bytes_per_frame, 'frames_per_launch': frames_per_launch,
+                'avg_launch_ms': per_launch_ms,
+                'dominant_kernel': {'name': 'gauss_decide_kernel (K1b)', 'avg_launch_ms': k1b_ms,
+                                    'share_of_frontend': kb[0] / fe_ms if fe_ms > 0 else None,
+                                    'note': 'issue-bound (FP32 + integer pipes), reads 1 B/px and writes 0.25 B/px; see DESIGN.md section 4'},
                 'kernel_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
                 'whole_path_frac': (value * bytes_per_frame / 1e9) / (hbm_peak * world)}
 
@@ -337,7 +352,8 @@ def main():
         'config': {'workload': f'cfg2: 1228x922x{Cn} (BGR as cap.read() delivers) x {F} frames per GPU, {args.cells} rods, '
                                f'default tracking.ini (white-on-dark, offset 5, adaptive double threshold 2.0, gsff 10/20/30)',
                    'frames_per_gpu': F, 'batch': args.batch, 'l2': 'inputs (>= 10 GB) far exceed the 126 MB L2',
-                   'parallelism': f'frame-range x{world}, one sequential linker', 'rows': n_rows, 'tracks': n_tracks},
+                   'parallelism': f'frame-range x{world}, one sequential linker', 'rows': n_rows, 'tracks': n_tracks,
+                   'max_blobs': MB, 'max_tracks': MT},
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }
     print(json.dumps(line), flush=True)

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define YSMR_ABI_VERSION 1
+#define YSMR_ABI_VERSION 2
 
 enum {
     YSMR_OK = 0,
@@ -158,7 +158,14 @@ int64_t ysmr_launch_count(const ysmr_ctx *ctx);
 /* Per-kernel timing for bench.py's roofline: when enabled every kernel launch is bracketed by CUDA events on the stream
  * it is launched on.  ysmr_get_profile synchronises, writes the summed milliseconds and the number of launches per
  * kernel kind (arrays of YSMR_PROF_KINDS entries) and clears the record. */
-enum { YSMR_PROF_FRONTEND = 0, YSMR_PROF_LABEL = 1, YSMR_PROF_GEOMETRY = 2, YSMR_PROF_LINK = 3, YSMR_PROF_KINDS = 4 };
+enum {
+    YSMR_PROF_FRONTEND = 0,   /* all front-end launches of a batch together (K1a + margins + K1b + K1c) */
+    YSMR_PROF_LABEL = 1, YSMR_PROF_GEOMETRY = 2, YSMR_PROF_LINK = 3,
+    YSMR_PROF_K1A = 4,        /* blur pre-pass + margins */
+    YSMR_PROF_K1B = 5,        /* Gaussian + threshold decisions */
+    YSMR_PROF_K1C = 6,        /* mask packing */
+    YSMR_PROF_KINDS = 7
+};
 int ysmr_set_profiling(ysmr_ctx *ctx, int enabled);
 int ysmr_get_profile(ysmr_ctx *ctx, double *ms, int64_t *launches);
 /* With ysmr_set_profiling(ctx, 3) the linker's shared-memory path also accumulates SM cycles per phase (clock64 of

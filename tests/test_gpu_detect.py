@@ -82,6 +82,18 @@ def test_full_width_frames_all_modes(white, offset, adt, w):
     assert rep['rects'] > 50 and rep['rect_flip'] <= 1, rep
 
 
+@pytest.mark.parametrize('w', [333, 334, 336, 260])
+def test_bgr_true_colour_any_width(w):
+    """cvtColor + blur pre-pass on true-colour frames of widths that exercise the generic (unaligned) loads, the half-group
+    lane (w % 8 == 4) and the scalar-tail lanes of the Gaussian."""
+    rng = np.random.default_rng(w)
+    cfg = SceneConfig(width=w, height=120, n_frames=3, n_cells=10, seed=w, margin=15.0)
+    grey = render_frames(make_scene(cfg)).astype(np.int16)
+    bgr = np.stack([np.clip(grey + rng.integers(-20, 21, grey.shape), 0, 255) for _ in range(3)], -1).astype(np.uint8)
+    rep = _compare_stages(np.ascontiguousarray(bgr), ref_stages.DetectSettings(True, 5, 2.0), channels=3)
+    assert rep['rect_flip'] <= 1, rep
+
+
 def test_cfg1_full_frames_bgr():
     cfg = SceneConfig(n_frames=4)
     grey = render_frames(make_scene(cfg))

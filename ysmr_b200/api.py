@@ -209,7 +209,7 @@ class Context:
     def launch_count(self):
         return int(self.lib.ysmr_launch_count(self._h))
 
-    PROF_KINDS = ('frontend', 'label', 'geometry', 'link')
+    PROF_KINDS = ('frontend', 'label', 'geometry', 'link', 'k1a', 'k1b', 'k1c')
 
     def set_profiling(self, enabled=True, link_phases=False):
         self._check(self.lib.ysmr_set_profiling(self._h, (1 if enabled else 0) | (2 if link_phases else 0)))
@@ -221,6 +221,6 @@ class Context:
 
     def get_profile(self):
         """{kind: (total_ms, launches)} since the last call; synchronises the device."""
-        ms = (C.c_double * 4)(); n = (C.c_int64 * 4)()
+        ms = (C.c_double * 7)(); n = (C.c_int64 * 7)()
         self._check(self.lib.ysmr_get_profile(self._h, ms, n))
         return {k: (ms[i], n[i]) for i, k in enumerate(self.PROF_KINDS)}

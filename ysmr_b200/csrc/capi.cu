@@ -50,10 +50,8 @@ struct ysmr_ctx {
     int window = 0;               // mean/std moving window (frames)
     int gains_affine = 1;         // all uploaded FIR gains are affine in the tap index (required by the fast linker)
     int link_fast = 1;            // YSMR_LINK=general disables the shared-memory fast path of the linker (tests)
-    int fused_bgr = 0;            // YSMR_BGR=fused: luma inside the strip kernel instead of the grey pre-pass
-    uint8_t *grey = nullptr;      // [max_batch][h][w] grey planes of 3-channel input
     int use_tile = 0;             // YSMR_FRONTEND=tile: run the simple tile kernel instead of the production kernels
-    int use_strip = 0;            // YSMR_FRONTEND=strip: previous-generation strip kernel (kept for A/B timing)
+    cudaStream_t s_tail = nullptr; cudaEvent_t ev_tail_fork = nullptr, ev_tail_join = nullptr;   // K1b tail-strip launch
     uint8_t *plane = nullptr; int64_t plane_stride = 0; int pitch = 0;          // blurred planes (K1a -> K1b)
     uint8_t *decisions = nullptr; int64_t dec_stride = 0; int dec_pitch = 0;    // decision bytes (K1b -> K1c)
     std::string err;
@@ -195,8 +193,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     ysmr_ctx *c = new ysmr_ctx();
     c->device = device; c->h = height; c->w = width; c->ww = (width + 31) / 32; c->channels = channels; c->p = *params;
     derive_thresholds(c);
-    { const char *fe = getenv("YSMR_FRONTEND"); c->use_tile = fe && strcmp(fe, "tile") == 0; c->use_strip = fe && strcmp(fe, "strip") == 0; }
-    { const char *bg = getenv("YSMR_BGR"); c->fused_bgr = bg && strcmp(bg, "fused") == 0; }
+    { const char *fe = getenv("YSMR_FRONTEND"); c->use_tile = fe && strcmp(fe, "tile") == 0; }
     { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strcmp(lk, "general") == 0); }
 #define CC(expr)                                                                                                       \
     do {                                                                                                               \
@@ -211,7 +208,6 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     const size_t B = (size_t)params->max_batch, H = (size_t)height, WW = (size_t)c->ww, MB = (size_t)params->max_blobs;
     CC(dev_alloc(c, &c->mask_bits, B * H * WW));
     CC(dev_alloc(c, &c->marker_bits, B * H * WW));
-    if (channels == 3 && c->use_strip) CC(dev_alloc(c, &c->grey, B * H * (size_t)width));
     c->pitch = 16 + ((width + 127) / 128) * 128;
     c->plane_stride = (int64_t)(height + 10) * c->pitch;
     CC(dev_alloc(c, &c->plane, B * (size_t)c->plane_stride));
@@ -288,6 +284,9 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     CC(launch_link_reset(ls, params->max_tracks, nullptr)); c->launches++;
     CC(cudaDeviceSynchronize());
     // pipeline objects
+    CC(cudaStreamCreateWithFlags(&c->s_tail, cudaStreamNonBlocking));
+    CC(cudaEventCreateWithFlags(&c->ev_tail_fork, cudaEventDisableTiming));
+    CC(cudaEventCreateWithFlags(&c->ev_tail_join, cudaEventDisableTiming));
     CC(cudaStreamCreateWithFlags(&c->s_copy, cudaStreamNonBlocking));
     CC(cudaStreamCreateWithFlags(&c->s_det, cudaStreamNonBlocking));
     {
@@ -328,6 +327,9 @@ int ysmr_destroy(ysmr_ctx *c)
     }
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
+    if (c->ev_tail_fork) cudaEventDestroy(c->ev_tail_fork);
+    if (c->ev_tail_join) cudaEventDestroy(c->ev_tail_join);
+    if (c->s_tail) cudaStreamDestroy(c->s_tail);
     if (c->s_copy) cudaStreamDestroy(c->s_copy);
     if (c->s_det) cudaStreamDestroy(c->s_det);
     if (c->s_link) cudaStreamDestroy(c->s_link);
@@ -397,22 +399,19 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
         ProfScope ps(c, c->use_tile ? YSMR_PROF_FRONTEND : YSMR_PROF_GEOMETRY, st);
         CU(c, launch_frontend_tile(fp, st)); c->launches++;
     }
-    if (!c->use_tile && !c->use_strip) {
+    if (!c->use_tile) {
         ProfScope ps(c, YSMR_PROF_FRONTEND, st);
-        int nl = 0;
-        CU(c, launch_frontend_v3(fp, st, &nl)); c->launches += nl;
-    }
-    if (c->use_strip) {
-        ProfScope ps(c, YSMR_PROF_FRONTEND, st);
-        if (c->channels == 3 && !c->fused_bgr) {
-            // cvtColor as a streaming pre-pass, then the single-channel strip kernel on the grey planes
-            CU(c, launch_bgr_to_grey(d_frames, frame_stride, c->grey, c->h, c->w, n_frames, st)); c->launches++;
-            FrontParams fg = fp;
-            fg.frames = c->grey; fg.frame_stride = (int64_t)c->h * c->w; fg.channels = 1;
-            CU(c, launch_frontend_strip(fg, st)); c->launches++;
-        } else {
-            CU(c, launch_frontend_strip(fp, st)); c->launches++;
+        { ProfScope p1(c, YSMR_PROF_K1A, st); CU(c, launch_blur_prepass(fp, st)); c->launches += 2; }
+        {
+            ProfScope p2(c, YSMR_PROF_K1B, st);
+            int nl = 0;
+            CU(c, cudaEventRecord(c->ev_tail_fork, st));
+            CU(c, cudaStreamWaitEvent(c->s_tail, c->ev_tail_fork, 0));
+            CU(c, launch_gauss_decide(fp, st, c->s_tail, &nl)); c->launches += nl;
+            CU(c, cudaEventRecord(c->ev_tail_join, c->s_tail));
+            CU(c, cudaStreamWaitEvent(st, c->ev_tail_join, 0));
         }
+        { ProfScope p3(c, YSMR_PROF_K1C, st); CU(c, launch_pack_masks(fp, st)); c->launches += 1; }
     }
     const int64_t rows = (int64_t)n_frames * c->h;
     if (dbg && dbg->d_mask) { CU(c, launch_unpack_bits(c->mask_bits, dbg->d_mask, rows, c->w, c->ww, st)); c->launches++; }

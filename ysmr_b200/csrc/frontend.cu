@@ -10,8 +10,7 @@
 //
 // This file holds two implementations that must agree bit for bit:
 //   frontend_tile_kernel   -- straightforward shared-memory tiles, can also dump every intermediate stage (debug);
-//   frontend_strip_kernel  -- the production kernel: each warp marches a 128-column strip down the frame with the
-//                             11-row column window in registers, 128-bit shared-memory traffic and packed stores.
+//   K1a / K1b / K1c        -- the production kernels (blur pre-pass, Gaussian + decisions, mask packing), see below.
 #include "frontend.cuh"
 
 namespace ysmr {
@@ -124,28 +123,8 @@ __global__ void __launch_bounds__(256) frontend_tile_kernel(FrontParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// Strip kernel (production)
-//
-// Work item = (frame, 128-column strip, row chunk), one per WARP; warps never synchronise with each other.
-// Lane l owns the 4 adjacent columns x0 = xs + 4l.  The warp walks down the rows; step s handles blurred row
-// br = y0 - 5 + s (clamped: BORDER_REPLICATE of the Gaussian):
-//   grey rows br-1, br, br+1 (REFLECT_101) live in three packed registers (u8x4) that slide down;
-//   vertical 1-2-1 sums in packed 16-bit lanes, horizontal neighbours by shuffle, blurred -> float -> shared row buffer;
-//   row pass of the 11-tap Gaussian from 5 x LDS.128 (OpenCV's FMA order), result into an 11-row register window;
-//   column pass for output row y0 + s - 10 from that window, rint via the 1.5*2^23 trick, two integer compares against
-//   the blurred value queued 5 steps ago, nibbles OR-reduced over 8 lanes into mask words.
-// Steps are unrolled by 11 (= window depth) so that every window index is a compile-time constant.  The 2 x 5 halo
-// columns the strip needs from its neighbours are produced once per 11 steps by 22 otherwise idle lanes ("halo pass").
+// Shared pieces of the production kernels
 // ---------------------------------------------------------------------------------------------------------------------
-constexpr int STRIP_W = 128;
-#ifndef STRIP_WARPS_N
-#define STRIP_WARPS_N 4
-#endif
-#ifndef STRIP_MINBLOCKS
-#define STRIP_MINBLOCKS 4
-#endif
-constexpr int STRIP_WARPS = STRIP_WARPS_N;
-constexpr int ROWBUF_W = STRIP_W + 16;            // 8 halo floats each side (5 used), keeps LDS.128 aligned
 constexpr float KG0 = 0.00881223008f, KG1 = 0.0271435864f, KG2 = 0.0651140586f, KG3 = 0.121649072f, KG4 = 0.176998362f,
                 KG5 = 0.200565413f;
 
@@ -155,40 +134,6 @@ __device__ __forceinline__ uint32_t grey_px(const uint8_t *frame, int w, int y, 
     const uint8_t *p = frame + ((int64_t)y * w + x) * C;
     if (C == 3) return luma(p[0], p[1], p[2]);
     return p[0];
-}
-
-// 4 grey pixels x0..x0+3 of row y packed little-endian (pixel x0 in bits 0-7).  fast: all four inside the image and the
-// address 4-byte aligned; otherwise per-pixel loads with REFLECT_101 (+ clamp for lanes hanging over the right edge).
-template <int C>
-__device__ __forceinline__ uint32_t load_grey4(const uint8_t *frame, int w, int y, int x0, bool fast)
-{
-    if (fast) {
-        const uint32_t *q = reinterpret_cast<const uint32_t *>(frame + ((int64_t)y * w + x0) * C);
-        if (C == 1) return __ldg(q);
-        // 12 bytes B0 G0 R0 B1 | G1 R1 B2 G2 | R2 B3 G3 R3.  The Q15 luma weights 3735, 19235, 9798 are split into high
-        // and low bytes (14,75,38 / 151,35,70) so that each pixel costs two byte dot products:
-        // (3735 B + 19235 G + 9798 R + 16384) >> 15 == (256 * dp4a(px, hi) + dp4a(px, lo) + 16384) >> 15, exactly.
-        const uint32_t w0 = __ldg(q), w1 = __ldg(q + 1), w2 = __ldg(q + 2);
-        const uint32_t p1 = __byte_perm(w0, w1, 0x0543);          // B1 G1 R1 (then B0, weight 0)
-        const uint32_t p2 = __byte_perm(w1, w2, 0x0432);          // B2 G2 R2
-        constexpr uint32_t HI = 14u | (75u << 8) | (38u << 16), LO = 151u | (35u << 8) | (70u << 16);
-        const uint32_t g0 = (__dp4a(w0, HI, 0u) * 256u + __dp4a(w0, LO, 16384u)) >> 15;
-        const uint32_t g1 = (__dp4a(p1, HI, 0u) * 256u + __dp4a(p1, LO, 16384u)) >> 15;
-        const uint32_t g2 = (__dp4a(p2, HI, 0u) * 256u + __dp4a(p2, LO, 16384u)) >> 15;
-        const uint32_t g3 = (__dp4a(w2, HI << 8, 0u) * 256u + __dp4a(w2, LO << 8, 16384u)) >> 15;   // B3 G3 R3 sit in bytes 1-3
-        return g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
-    }
-    uint32_t r = 0;
-#pragma unroll
-    for (int k = 0; k < 4; ++k) r |= grey_px<C>(frame, w, y, reflect101(x0 + k, w)) << (8 * k);
-    return r;
-}
-
-__device__ __forceinline__ float u8_to_float(uint32_t packed16, int half)
-{
-    // exact int -> float without the conversion pipe: 0x4B000000 | v is 8388608 + v
-    const uint32_t bits = __byte_perm(packed16, 0x4B000000u, half ? 0x7442 : 0x7440);
-    return __uint_as_float(bits) - 8388608.0f;
 }
 
 template <bool TAIL>
@@ -270,251 +215,6 @@ __device__ __forceinline__ float gauss_col(float c, float m1, float p1, float m2
     acc = __fmaf_rn(KG4, s1, acc); acc = __fmaf_rn(KG3, s2, acc); acc = __fmaf_rn(KG2, s3, acc);
     acc = __fmaf_rn(KG1, s4, acc); acc = __fmaf_rn(KG0, s5, acc);
     return acc;
-}
-
-struct StripTask {
-    int frame, strip, y0, y1;
-};
-
-// One step of the register window: store this step's row-pass results / blurred pixels in slot J and run the column
-// pass centred 5 steps back.  J is a template parameter so that every window index is a compile-time constant; the
-// caller dispatches on (step % 11) with a switch, which keeps the rest of the step loop un-unrolled (a fully unrolled
-// body would be ~45 KB of code and thrash the instruction cache).
-template <int J, bool TAIL>
-__device__ __forceinline__ void window_step(float2 (&win)[11][2], uint32_t (&bq)[11], const float (&r)[4], uint32_t bcur,
-                                            bool col_tail, float (&m)[4], uint32_t &bc)
-{
-    constexpr int c = (J + 6) % 11;            // (J - 5) mod 11
-    win[J][0] = make_float2(r[0], r[1]); win[J][1] = make_float2(r[2], r[3]);
-    bq[J] = bcur;                              // blurred px0..px3 as bytes
-    bc = bq[c];
-#pragma unroll
-    for (int k = 0; k < 2; ++k) {
-        const float2 v = gauss_col2<TAIL>(win[c][k], win[(c + 10) % 11][k], win[(c + 1) % 11][k], win[(c + 9) % 11][k],
-                                          win[(c + 2) % 11][k], win[(c + 8) % 11][k], win[(c + 3) % 11][k], win[(c + 7) % 11][k],
-                                          win[(c + 4) % 11][k], win[(c + 6) % 11][k], win[(c + 5) % 11][k], col_tail);
-        m[2 * k] = v.x; m[2 * k + 1] = v.y;
-    }
-}
-
-// Image-border variant of halo_side (first strip's left side, last strip's right side): every column index is clamped /
-// reflected individually.  Rare, so kept out of line and un-unrolled to keep the hot code small.
-template <int C>
-__device__ __noinline__ void halo_side_border(const uint8_t *frame, int w, int h, int br, int xs, int side, float *dst, uint32_t *vh_out)
-{
-    const int ym = reflect101(br - 1, h), yp = reflect101(br + 1, h);
-    const int xb = side ? xs + STRIP_W : xs - 5;
-#pragma unroll 1
-    for (int k = 0; k < 5; ++k) {
-        const int cx = clampi(xb + k, w);
-        int sum = 0;
-#pragma unroll 1
-        for (int dx = -1; dx <= 1; ++dx) {
-            const int x = reflect101(cx + dx, w);
-            const int v = (int)grey_px<C>(frame, w, ym, x) + 2 * (int)grey_px<C>(frame, w, br, x) + (int)grey_px<C>(frame, w, yp, x);
-            sum += dx == 0 ? 2 * v : v;
-        }
-        dst[k] = (float)((sum + 8) >> 4);
-    }
-    const int xa = reflect101(side ? xs + STRIP_W : xs - 1, w);
-    *vh_out = (uint32_t)((int)grey_px<C>(frame, w, ym, xa) + 2 * (int)grey_px<C>(frame, w, br, xa) + (int)grey_px<C>(frame, w, yp, xa));
-}
-
-// Halo pass for one (step, side): blurred at the 5 columns next to the strip (clamped = BORDER_REPLICATE of the Gaussian;
-// neighbours with REFLECT_101 = border of the 3x3 blur) and the vertical sum of the adjacent column.
-template <int C>
-__device__ __forceinline__ void halo_side(const uint8_t *frame, int w, int h, int br, int xs, int side, float *dst, uint32_t *vh_out)
-{
-    const int ym = reflect101(br - 1, h), yp = reflect101(br + 1, h);
-    const int xb = side ? xs + STRIP_W : xs - 5;          // first of the 5 blurred columns
-    auto vsum = [&](int x) -> int {
-        return (int)grey_px<C>(frame, w, ym, x) + 2 * (int)grey_px<C>(frame, w, br, x) + (int)grey_px<C>(frame, w, yp, x);
-    };
-    if (xb - 1 >= 0 && xb + 5 < w) {
-        int v[7];
-#pragma unroll
-        for (int k = 0; k < 7; ++k) v[k] = vsum(xb - 1 + k);
-#pragma unroll
-        for (int k = 0; k < 5; ++k) dst[k] = (float)((v[k] + 2 * v[k + 1] + v[k + 2] + 8) >> 4);
-        *vh_out = (uint32_t)(side ? v[1] : v[5]);          // column xs+128 resp. xs-1
-    } else {
-        halo_side_border<C>(frame, w, h, br, xs, side, dst, vh_out);
-    }
-}
-
-template <int C, bool EDGE>
-__device__ __forceinline__ void strip_run(const FrontParams &p, const StripTask t, float (*rowbuf)[ROWBUF_W], uint32_t (*vh)[2])
-{
-    const int lane = threadIdx.x & 31;
-    const int xs = t.strip * STRIP_W;
-    const int x0 = xs + 4 * lane;
-    const uint8_t *frame = p.frames + (int64_t)t.frame * p.frame_stride;
-    const int w = p.w, h = p.h;
-    // fast loads: the lane's 4 pixels are inside the image and 4-byte aligned in every row
-    const bool aligned = ((reinterpret_cast<uintptr_t>(frame) & 3) == 0) && (((int64_t)w * C) % 4 == 0);
-    const bool fast = aligned && (x0 + 3 < w);
-    const bool row_tail = EDGE && (x0 >= p.row_tail_from);
-    const bool col_tail = EDGE && (x0 >= p.col_tail_from);
-    uint32_t valid_nib = 0xFu;                // interior strips: all four pixels of every lane are inside the image
-    if (EDGE) {
-        valid_nib = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) valid_nib |= (x0 + k < w) ? (1u << k) : 0u;
-    }
-    const uint32_t inv_nib = (p.inverted ? 0xFu : 0u) & valid_nib;
-    const int shift = 4 * (lane & 7);
-    const int word = (xs >> 5) + (lane >> 3);
-    const bool scalar_mode = p.scalar_thr != nullptr;
-    // Packed compare (two pixels per 32-bit add, 16-bit lanes): X = B + K - M with B = blurred pair, M = mean pair and
-    // K = 0x8000 - t - 1 per lane; bit 15 of a lane is set iff b - mean - t - 1 >= 0, i.e. d > t.  In the mean/std mode the
-    // mean is replaced by 0 and t by the frame's scalar threshold (cv2.threshold: src > T).
-    auto lim = [](int v) { return v < -30000 ? -30000 : (v > 30000 ? 30000 : v); };   // keeps the 16-bit lanes apart
-    const int t_a = lim(scalar_mode ? p.scalar_thr[t.frame] : p.t_mask);
-    const int t_b = lim(scalar_mode ? 30000 : p.t_marker);       // marker image unused in the mean/std mode
-    const uint32_t k_a = (uint32_t)((0x8000 - t_a - 1) & 0xFFFF) * 0x00010001u;
-    const uint32_t k_b = (uint32_t)((0x8000 - t_b - 1) & 0xFFFF) * 0x00010001u;
-    const uint32_t mean_keep = scalar_mode ? 0u : 0xFFFFFFFFu;
-    // REPLICATE source for pixels right of the image (EDGE strips only)
-    const int e_owner = (w - 1 - xs) >> 2, e_pos = (w - 1 - xs) & 3;
-
-    float2 win[11][2];                // row-pass results of the last 11 steps, as pixel pairs (px0,px1), (px2,px3)
-    uint32_t bq[11];                  // blurred (u8x4) of the last 11 steps
-#pragma unroll
-    for (int i = 0; i < 11; ++i) { bq[i] = 0; win[i][0] = win[i][1] = make_float2(0.f, 0.f); }
-
-    const int n_steps = (t.y1 - t.y0) + 10;
-    int cbr = clampi(t.y0 - 5, h);    // clamped blurred row of the current step
-    uint32_t gp = load_grey4<C>(frame, w, reflect101(cbr - 1, h), x0, fast);   // grey rows br-1, br, br+1
-    uint32_t gc = load_grey4<C>(frame, w, cbr, x0, fast);
-    uint32_t gn = load_grey4<C>(frame, w, reflect101(cbr + 1, h), x0, fast);
-    uint32_t pre = 0;
-    // output pointers of row y0 - 10 + s (advance by one row per step; only dereferenced for s >= 10)
-    uint32_t *out_mask = p.mask_bits + ((int64_t)t.frame * h + (t.y0 - 10)) * p.ww + word;
-    uint32_t *out_mark = p.marker_bits ? p.marker_bits + ((int64_t)t.frame * h + (t.y0 - 10)) * p.ww + word : nullptr;
-    const bool writer = (lane & 7) == 0 && word < p.ww;
-    const int ww = p.ww;
-
-    int j = 0;
-    for (int s = 0; s < n_steps; ++s) {
-        if (j == 0) {
-            // halo pass for steps s .. s+10: lanes 0..21 = (step, side)
-            __syncwarp();
-            if (lane < 22) {
-                const int jj = lane >> 1, side = lane & 1;
-                halo_side<C>(frame, w, h, clampi(t.y0 - 5 + s + jj, h), xs, side, &rowbuf[jj][side ? 8 + STRIP_W : 3], &vh[jj][side]);
-            }
-            __syncwarp();
-        }
-        // prefetch the grey row the NEXT step will need (if it advances)
-        const int next_cbr = clampi(t.y0 - 5 + s + 1, h);
-        const bool adv_next = next_cbr != cbr;
-        if (adv_next) pre = load_grey4<C>(frame, w, reflect101(next_cbr + 1, h), x0, fast);
-
-        // vertical 1-2-1 sums, packed 16-bit: lo = (px0, px1), hi = (px2, px3)
-        const uint32_t v_lo = __byte_perm(gp, 0, 0x4140) + 2 * __byte_perm(gc, 0, 0x4140) + __byte_perm(gn, 0, 0x4140);
-        const uint32_t v_hi = __byte_perm(gp, 0, 0x4342) + 2 * __byte_perm(gc, 0, 0x4342) + __byte_perm(gn, 0, 0x4342);
-        uint32_t left = __shfl_up_sync(0xffffffffu, v_hi, 1) >> 16;
-        uint32_t right = __shfl_down_sync(0xffffffffu, v_lo, 1) & 0xFFFFu;
-        const uint2 vhj = *reinterpret_cast<const uint2 *>(vh[j]);       // broadcast load, then select: no branches
-        left = lane == 0 ? vhj.x : left;
-        right = lane == 31 ? vhj.y : right;
-        // (REFLECT_101 at the right image edge needs no special case: lanes that hang over the edge load their pixels with
-        //  reflected indices, so the sums of column w and beyond already are those of w-2, ...)
-        const uint32_t vm1_lo = (v_lo << 16) | left;                       // (v[-1], v0)
-        const uint32_t mid = __funnelshift_r(v_lo, v_hi, 16);              // (v1, v2)
-        const uint32_t vp1_hi = (v_hi >> 16) | (right << 16);              // (v3, v[4])
-        uint32_t b_lo = ((vm1_lo + 2 * v_lo + mid + 0x00080008u) >> 4) & 0x00FF00FFu;   // blurred px0, px1
-        uint32_t b_hi = ((mid + 2 * v_hi + vp1_hi + 0x00080008u) >> 4) & 0x00FF00FFu;   // blurred px2, px3
-        if (EDGE) {
-            // BORDER_REPLICATE of the blurred image for pixels right of the image: value of column w-1
-            const uint32_t src = e_pos < 2 ? b_lo : b_hi;
-            const uint32_t mine = (e_pos & 1) ? (src >> 16) : (src & 0xFFFFu);
-            const uint32_t edge = __shfl_sync(0xffffffffu, mine, e_owner);
-            if (x0 + 0 >= w) b_lo = (b_lo & 0xFFFF0000u) | edge;
-            if (x0 + 1 >= w) b_lo = (b_lo & 0x0000FFFFu) | (edge << 16);
-            if (x0 + 2 >= w) b_hi = (b_hi & 0xFFFF0000u) | edge;
-            if (x0 + 3 >= w) b_hi = (b_hi & 0x0000FFFFu) | (edge << 16);
-        }
-        const uint32_t bcur = __byte_perm(b_lo, b_hi, 0x6420);
-        float4 f;
-        f.x = u8_to_float(b_lo, 0); f.y = u8_to_float(b_lo, 1); f.z = u8_to_float(b_hi, 0); f.w = u8_to_float(b_hi, 1);
-        float *rb = rowbuf[j];
-        *reinterpret_cast<float4 *>(&rb[8 + 4 * lane]) = f;
-        __syncwarp();
-        float a[20];
-#pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            const float4 t4 = *reinterpret_cast<const float4 *>(&rb[4 * lane + 4 * q]);
-            a[4 * q] = t4.x; a[4 * q + 1] = t4.y; a[4 * q + 2] = t4.z; a[4 * q + 3] = t4.w;
-        }
-        float r[4], m[4];
-#pragma unroll
-        for (int k = 0; k < 4; ++k) r[k] = gauss_row<EDGE>(&a[3 + k], row_tail);
-        uint32_t bc;
-        switch (j) {
-            case 0: window_step<0, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 1: window_step<1, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 2: window_step<2, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 3: window_step<3, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 4: window_step<4, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 5: window_step<5, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 6: window_step<6, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 7: window_step<7, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 8: window_step<8, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            case 9: window_step<9, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-            default: window_step<10, EDGE>(win, bq, r, bcur, col_tail, m, bc); break;
-        }
-        // ---- compare for output row y = y0 + s - 10 (centre = step s-5)
-        // rint (half to even) by adding 1.5 * 2^23: the low 16 bits of the float's bit pattern are the rounded mean
-        const uint32_t i0 = __float_as_uint(__fadd_rn(m[0], 12582912.0f)), i1 = __float_as_uint(__fadd_rn(m[1], 12582912.0f));
-        const uint32_t i2 = __float_as_uint(__fadd_rn(m[2], 12582912.0f)), i3 = __float_as_uint(__fadd_rn(m[3], 12582912.0f));
-        const uint32_t mean_lo = __byte_perm(i0, i1, 0x5410) & mean_keep;       // (mean0, mean1) as 16-bit lanes
-        const uint32_t mean_hi = __byte_perm(i2, i3, 0x5410) & mean_keep;
-        const uint32_t bl = __byte_perm(bc, 0, 0x4140), bh = __byte_perm(bc, 0, 0x4342);
-        const uint32_t xa_lo = bl + k_a - mean_lo, xa_hi = bh + k_a - mean_hi;
-        const uint32_t xb_lo = bl + k_b - mean_lo, xb_hi = bh + k_b - mean_hi;
-        // gather bits 15 / 31 of the two registers into a nibble: bytes 1 and 3 -> flags in bit 7 of four bytes -> multiply
-        auto nibble = [](uint32_t lo, uint32_t hi) -> uint32_t {
-            const uint32_t y = (__byte_perm(lo, hi, 0x7531) >> 7) & 0x01010101u;
-            return (y * 0x01020408u) >> 24;
-        };
-        uint32_t nib_mask = (nibble(xa_lo, xa_hi) & valid_nib) ^ inv_nib;
-        uint32_t nib_mark = (nibble(xb_lo, xb_hi) & valid_nib) ^ inv_nib;
-        uint32_t wm = nib_mask << shift, wk = nib_mark << shift;
-        wm |= __shfl_xor_sync(0xffffffffu, wm, 1); wk |= __shfl_xor_sync(0xffffffffu, wk, 1);
-        wm |= __shfl_xor_sync(0xffffffffu, wm, 2); wk |= __shfl_xor_sync(0xffffffffu, wk, 2);
-        wm |= __shfl_xor_sync(0xffffffffu, wm, 4); wk |= __shfl_xor_sync(0xffffffffu, wk, 4);
-        if (s >= 10 && writer) {
-            *out_mask = wm;
-            if (out_mark) *out_mark = wk;
-        }
-        out_mask += ww;
-        if (out_mark) out_mark += ww;
-        // slide the grey window
-        if (adv_next) { gp = gc; gc = gn; gn = pre; cbr = next_cbr; }
-        j = j == 10 ? 0 : j + 1;
-    }
-}
-
-template <int C>
-__global__ void __launch_bounds__(STRIP_WARPS * 32, STRIP_MINBLOCKS) frontend_strip_kernel(FrontParams p, int n_strips, int n_chunks, int rows_per_chunk)
-{
-    __shared__ __align__(16) float rowbuf[STRIP_WARPS][11][ROWBUF_W];
-    __shared__ uint32_t vh[STRIP_WARPS][11][2];
-    const int warp = threadIdx.x >> 5;
-    const int64_t task = (int64_t)blockIdx.x * STRIP_WARPS + warp;
-    const int64_t per_frame = (int64_t)n_strips * n_chunks;
-    if (task >= per_frame * p.n_frames) return;
-    StripTask t;
-    t.frame = (int)(task / per_frame);
-    const int r = (int)(task - (int64_t)t.frame * per_frame);
-    t.strip = r % n_strips;                   // neighbouring warps take neighbouring strips of the same rows (L1/L2 reuse)
-    const int chunk = r / n_strips;
-    t.y0 = chunk * rows_per_chunk;
-    t.y1 = min(p.h, t.y0 + rows_per_chunk);
-    const bool edge = (t.strip == n_strips - 1);       // the only strip that can hang over the right image edge
-    if (edge) strip_run<C, true>(p, t, rowbuf[warp], vh[warp]);
-    else strip_run<C, false>(p, t, rowbuf[warp], vh[warp]);
 }
 
 // =====================================================================================================================
@@ -924,50 +624,6 @@ __global__ void __launch_bounds__(256) pack_masks_kernel(FrontParams p)
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// BGR -> grey pre-pass (cv2.cvtColor, track_eval.py:180).  Streaming kernel: 8 pixels (24 bytes in, 8 bytes out) per
-// thread with 64-bit accesses.  Used in front of the strip kernel for 3-channel input: doing the luma inside the strip
-// kernel costs more than this pass (strided 12-byte loads per lane, luma repeated in the halo pass, register pressure).
-// ---------------------------------------------------------------------------------------------------------------------
-
-__global__ void __launch_bounds__(256) bgr_to_grey_kernel(const uint8_t *frames, int64_t frame_stride, uint8_t *grey, int64_t px_per_frame,
-                                                          int n_frames, int vec_ok)
-{
-    const int64_t groups = (px_per_frame + 7) / 8;
-    const int64_t total = groups * n_frames;
-    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t f = i / groups, g = i - f * groups;
-        const uint8_t *src = frames + f * frame_stride + g * 24;
-        uint8_t *dst = grey + f * px_per_frame + g * 8;
-        const int64_t left = px_per_frame - g * 8;
-        if (vec_ok && left >= 8) {
-            const uint2 a = __ldg(reinterpret_cast<const uint2 *>(src));
-            const uint2 b = __ldg(reinterpret_cast<const uint2 *>(src) + 1);
-            const uint2 c = __ldg(reinterpret_cast<const uint2 *>(src) + 2);
-            // bytes: a.x = B0 G0 R0 B1, a.y = G1 R1 B2 G2, b.x = R2 B3 G3 R3, b.y = B4 G4 R4 B5, c.x = G5 R5 B6 G6, c.y = R6 B7 G7 R7
-            const uint32_t g0 = luma_dp(a.x), g1 = luma_dp(__byte_perm(a.x, a.y, 0x0543)), g2 = luma_dp(__byte_perm(a.y, b.x, 0x0432)),
-                           g3 = luma_dp(b.x >> 8);
-            const uint32_t g4 = luma_dp(b.y), g5 = luma_dp(__byte_perm(b.y, c.x, 0x0543)), g6 = luma_dp(__byte_perm(c.x, c.y, 0x0432)),
-                           g7 = luma_dp(c.y >> 8);
-            uint2 o;
-            o.x = g0 | (g1 << 8) | (g2 << 16) | (g3 << 24);
-            o.y = g4 | (g5 << 8) | (g6 << 16) | (g7 << 24);
-            *reinterpret_cast<uint2 *>(dst) = o;
-        } else {
-            for (int k = 0; k < 8 && k < left; ++k) dst[k] = (uint8_t)luma(src[3 * k], src[3 * k + 1], src[3 * k + 2]);
-        }
-    }
-}
-
-cudaError_t launch_bgr_to_grey(const uint8_t *frames, int64_t frame_stride, uint8_t *grey, int h, int w, int n_frames, cudaStream_t st)
-{
-    const int64_t px = (int64_t)h * w;
-    const int vec_ok = ((reinterpret_cast<uintptr_t>(frames) & 7) == 0) && (frame_stride % 8 == 0) && ((reinterpret_cast<uintptr_t>(grey) & 7) == 0) &&
-                       (px % 8 == 0);
-    bgr_to_grey_kernel<<<148 * 16, 256, 0, st>>>(frames, frame_stride, grey, px, n_frames, vec_ok);
-    return cudaGetLastError();
-}
-
-// ---------------------------------------------------------------------------------------------------------------------
 // Small helpers used by the debug path and the mean/std mode
 // ---------------------------------------------------------------------------------------------------------------------
 __global__ void unpack_bits_kernel(const uint32_t *bits, uint8_t *bytes, int64_t rows, int w, int ww)
@@ -1062,90 +718,81 @@ cudaError_t launch_frontend_tile(const FrontParams &p, cudaStream_t st)
     return cudaGetLastError();
 }
 
-cudaError_t launch_frontend_strip(const FrontParams &p, cudaStream_t st)
+// K1a + margins (2 launches)
+cudaError_t launch_blur_prepass(const FrontParams &p, cudaStream_t st)
 {
-    const int n_strips = (p.w + STRIP_W - 1) / STRIP_W;
-    int n_chunks = (p.h + 115) / 230;
-    if (n_chunks < 1) n_chunks = 1;
+    const int n_strips = (p.w + PB_COLS - 1) / PB_COLS;
+    const int n_chunks = (p.h + 47) / 48;
     const int rows_per_chunk = (p.h + n_chunks - 1) / n_chunks;
     const int64_t tasks = (int64_t)n_strips * n_chunks * p.n_frames;
-    const unsigned grid = (unsigned)((tasks + STRIP_WARPS - 1) / STRIP_WARPS);
-    if (p.channels == 3) frontend_strip_kernel<3><<<grid, STRIP_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
-    else frontend_strip_kernel<1><<<grid, STRIP_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
-    return cudaGetLastError();
-}
-
-cudaError_t launch_frontend_v3(const FrontParams &p, cudaStream_t st, int *n_launched)
-{
-    int launched = 2;                                 // K1a + margins
-    // K1a
-    {
-        const int n_strips = (p.w + PB_COLS - 1) / PB_COLS;
-        const int n_chunks = (p.h + 47) / 48;
-        const int rows_per_chunk = (p.h + n_chunks - 1) / n_chunks;
-        const int64_t tasks = (int64_t)n_strips * n_chunks * p.n_frames;
-        const unsigned grid = (unsigned)((tasks + PB_WARPS - 1) / PB_WARPS);
-        const bool fast = (p.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.frames) & 3) == 0) && (p.frame_stride % 4 == 0);
-        if (p.channels == 3) {
-            if (fast) blur_prepass_kernel<3, true><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
-            else blur_prepass_kernel<3, false><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
-        } else {
-            if (fast) blur_prepass_kernel<1, true><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
-            else blur_prepass_kernel<1, false><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
-        }
-        cudaError_t e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-        plane_margins_kernel<<<148 * 4, 256, 0, st>>>(p);
-        e = cudaGetLastError();
-        if (e != cudaSuccess) return e;
-    }
-    // K1b
-    if (p.scalar_thr) {
-        scalar_decide_kernel<<<148 * 8, 256, 0, st>>>(p);
-        ++launched;
+    const unsigned grid = (unsigned)((tasks + PB_WARPS - 1) / PB_WARPS);
+    const bool fast = (p.w % 4 == 0) && ((reinterpret_cast<uintptr_t>(p.frames) & 3) == 0) && (p.frame_stride % 4 == 0);
+    if (p.channels == 3) {
+        if (fast) blur_prepass_kernel<3, true><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
+        else blur_prepass_kernel<3, false><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
     } else {
-        const int n_strips = (p.w + 127) / 128;
-        // strips from this one on contain scalar-tail columns (none if w % 8 == 0)
-        const int first_tail = p.col_tail_from < p.w ? p.col_tail_from / 128 : n_strips;
-        // row chunks: every chunk recomputes 10 halo rows, every wave of CTAs costs (rows + 10) steps -> pick the chunk count
-        // that minimises waves * (rows + 10) for this batch
-        static int ctas_per_sm = 0;
-        if (!ctas_per_sm) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, gauss_decide_kernel<false>, GD_WARPS * 32, 0);
-            if (ctas_per_sm < 1) ctas_per_sm = 1;
-        }
-        int sms = 148, dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const double slots = (double)sms * ctas_per_sm;
-        auto launch = [&](int first_strip, int ns, bool tail) -> cudaError_t {
-            if (ns <= 0) return cudaSuccess;
-            ++launched;
-            int best_chunks = 1; double best_cost = 1e300;
-            for (int nc = 1; nc <= 32 && nc * 16 <= p.h; ++nc) {
-                const int rows = (p.h + nc - 1) / nc;
-                const double ctas = (double)((int64_t)ns * nc * p.n_frames + GD_WARPS - 1) / GD_WARPS;
-                const double waves = ctas / slots;
-                const double cost = (waves < 1.0 ? 1.0 : (waves + 0.35)) * (rows + 10);  // +0.35: expected tail of a partial wave
-                if (cost < best_cost) { best_cost = cost; best_chunks = nc; }
-            }
-            const int n_chunks = best_chunks;
-            const int rows_per_chunk = (p.h + n_chunks - 1) / n_chunks;
-            const int64_t tasks = (int64_t)ns * n_chunks * p.n_frames;
-            const unsigned grid = (unsigned)((tasks + GD_WARPS - 1) / GD_WARPS);
-            if (tail) gauss_decide_kernel<true><<<grid, GD_WARPS * 32, 0, st>>>(p, first_strip, ns, n_chunks, rows_per_chunk);
-            else gauss_decide_kernel<false><<<grid, GD_WARPS * 32, 0, st>>>(p, first_strip, ns, n_chunks, rows_per_chunk);
-            return cudaGetLastError();
-        };
-        cudaError_t e1 = launch(0, first_tail, false);
-        if (e1 != cudaSuccess) return e1;
-        e1 = launch(first_tail, n_strips - first_tail, true);
-        if (e1 != cudaSuccess) return e1;
+        if (fast) blur_prepass_kernel<1, true><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
+        else blur_prepass_kernel<1, false><<<grid, PB_WARPS * 32, 0, st>>>(p, n_strips, n_chunks, rows_per_chunk);
     }
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) return e;
+    plane_margins_kernel<<<148 * 4, 256, 0, st>>>(p);
+    return cudaGetLastError();
+}
+
+// K1b: Gaussian + decisions (or the scalar threshold of the mean/std mode).  Strips [0, first_tail) run the tail-free
+// kernel on `st`; the strip(s) holding OpenCV's scalar-tail columns run the TAIL variant on `st_tail`, which the caller has
+// forked from `st` and joins afterwards, so that the small tail launch fills the gaps of the main launch's last wave.
+// *n_launched receives the number of kernels launched.
+cudaError_t launch_gauss_decide(const FrontParams &p, cudaStream_t st, cudaStream_t st_tail, int *n_launched)
+{
+    *n_launched = 0;
+    if (p.scalar_thr) {
+        scalar_decide_kernel<<<148 * 8, 256, 0, st>>>(p);
+        *n_launched = 1;
+        return cudaGetLastError();
+    }
+    const int n_strips = (p.w + 127) / 128;
+    const int first_tail = p.col_tail_from < p.w ? p.col_tail_from / 128 : n_strips;     // none if w % 8 == 0
+    // row chunks: every chunk recomputes 10 halo rows, every wave of CTAs costs (rows + 10) steps -> pick the chunk count
+    // that minimises waves * (rows + 10) for this batch
+    static int ctas_per_sm = 0;
+    if (!ctas_per_sm) {
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, gauss_decide_kernel<false>, GD_WARPS * 32, 0);
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+    }
+    int sms = 148, dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const double slots = (double)sms * ctas_per_sm;
+    auto launch = [&](int first_strip, int ns, bool tail, cudaStream_t s_) -> cudaError_t {
+        if (ns <= 0) return cudaSuccess;
+        ++*n_launched;
+        int best_chunks = 1; double best_cost = 1e300;
+        for (int nc = 1; nc <= 32 && nc * 16 <= p.h; ++nc) {
+            const int rows = (p.h + nc - 1) / nc;
+            const double ctas = (double)((int64_t)ns * nc * p.n_frames + GD_WARPS - 1) / GD_WARPS;
+            const double waves = ctas / slots;
+            const double cost = (waves < 1.0 ? 1.0 : (waves + 0.35)) * (rows + 10);  // +0.35: expected tail of a partial wave
+            if (cost < best_cost) { best_cost = cost; best_chunks = nc; }
+        }
+        const int n_chunks = best_chunks;
+        const int rows_per_chunk = (p.h + n_chunks - 1) / n_chunks;
+        const int64_t tasks = (int64_t)ns * n_chunks * p.n_frames;
+        const unsigned grid = (unsigned)((tasks + GD_WARPS - 1) / GD_WARPS);
+        if (tail) gauss_decide_kernel<true><<<grid, GD_WARPS * 32, 0, s_>>>(p, first_strip, ns, n_chunks, rows_per_chunk);
+        else gauss_decide_kernel<false><<<grid, GD_WARPS * 32, 0, s_>>>(p, first_strip, ns, n_chunks, rows_per_chunk);
+        return cudaGetLastError();
+    };
+    cudaError_t e = launch(first_tail, n_strips - first_tail, true, st_tail ? st_tail : st);
+    if (e != cudaSuccess) return e;
+    return launch(0, first_tail, false, st);
+}
+
+// K1c (1 launch)
+cudaError_t launch_pack_masks(const FrontParams &p, cudaStream_t st)
+{
     pack_masks_kernel<<<dim3((unsigned)((p.h * p.ww + 255) / 256), (unsigned)p.n_frames), 256, 0, st>>>(p);
-    if (n_launched) *n_launched = launched + 1;
     return cudaGetLastError();
 }
 

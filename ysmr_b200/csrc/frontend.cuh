@@ -29,9 +29,9 @@ struct FrontParams {
 };
 
 cudaError_t launch_frontend_tile(const FrontParams &p, cudaStream_t st);
-cudaError_t launch_frontend_strip(const FrontParams &p, cudaStream_t st);
-cudaError_t launch_frontend_v3(const FrontParams &p, cudaStream_t st, int *n_launched);
-cudaError_t launch_bgr_to_grey(const uint8_t *frames, int64_t frame_stride, uint8_t *grey, int h, int w, int n_frames, cudaStream_t st);
+cudaError_t launch_blur_prepass(const FrontParams &p, cudaStream_t st);      // K1a + margins: 2 launches
+cudaError_t launch_gauss_decide(const FrontParams &p, cudaStream_t st, cudaStream_t st_tail, int *n_launched);   // K1b
+cudaError_t launch_pack_masks(const FrontParams &p, cudaStream_t st);        // K1c: 1 launch
 cudaError_t launch_unpack_bits(const uint32_t *bits, uint8_t *bytes, int64_t rows, int w, int ww, cudaStream_t st);
 cudaError_t launch_frame_moments(const uint8_t *frames, int64_t stride, int n_frames, int h, int w, int channels,
                                  unsigned long long *sums, cudaStream_t st);
