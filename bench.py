@@ -48,50 +48,78 @@ def parse():
 
 # ---- clocks ------------------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
-         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+    """Samples SM clock and throttle reasons of one GPU every 10 ms from a thread (NVML); `mark()` brackets the timed region so
+    that only samples taken DURING it are reported.  Falls back to one nvidia-smi query when NVML is unavailable."""
 
     def __init__(self, gpu_index=0):
-        self.path = os.path.join(tempfile.gettempdir(), f'ysmr_clocks_{os.getpid()}.csv')
-        self.proc = None
         self.gpu = gpu_index
+        self.samples = []          # (t, sm_mhz, reasons_bitmask)
+        self.stop_flag = False
+        self.thread = None
+        self.max_mhz = None
+        self.t0 = self.t1 = None
+
+    def _run(self):
+        import pynvml as nv
+        h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+        while not self.stop_flag:
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                try:
+                    rs = nv.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((time.perf_counter(), float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.01)
 
     def start(self):
         try:
-            self.fh = open(self.path, 'w')
-            self.proc = subprocess.Popen(['nvidia-smi', f'--id={self.gpu}', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
-                                          '-lms', '100'], stdout=self.fh, stderr=subprocess.DEVNULL)
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML indexes physical devices; honour CUDA_VISIBLE_DEVICES when it is a plain index list
+            vis = os.environ.get('CUDA_VISIBLE_DEVICES')
+            if vis:
+                try:
+                    self.gpu = int(vis.split(',')[self.gpu])
+                except Exception:
+                    pass
+            h = nv.nvmlDeviceGetHandleByIndex(self.gpu)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._run, daemon=True)
+            self.thread.start()
         except Exception:
-            self.proc = None
+            self.thread = None
+
+    def mark(self, which):
+        if which == 0:
+            self.t0 = time.perf_counter()
+        else:
+            self.t1 = time.perf_counter()
 
     def stop(self):
         out = {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': []}
-        if self.proc is None:
+        if self.thread is not None:
+            self.stop_flag = True
+            self.thread.join(timeout=2)
+            inside = [x for x in self.samples if self.t0 is not None and self.t0 <= x[0] <= self.t1]
+            if not inside and self.samples and self.t0 is not None:      # very short region: nearest samples
+                mid = 0.5 * (self.t0 + self.t1)
+                inside = sorted(self.samples, key=lambda x: abs(x[0] - mid))[:3]
+            if inside:
+                names = {0x8: 'hw_slowdown', 0x40: 'hw_thermal_slowdown', 0x20: 'sw_thermal_slowdown', 0x4: 'sw_power_cap'}
+                bits = 0
+                for x in inside:
+                    bits |= x[2]
+                out = {'sm_mhz': float(np.median([x[1] for x in inside])), 'sm_max_mhz': self.max_mhz,
+                       'reasons': sorted(v for k, v in names.items() if bits & k), 'samples': len(inside)}
             return out
-        self.proc.terminate()
         try:
-            self.proc.wait(timeout=5)
+            q = subprocess.run(['nvidia-smi', f'--id={self.gpu}', '--query-gpu=clocks.sm,clocks.max.sm', '--format=csv,noheader,nounits'],
+                               capture_output=True, text=True, timeout=10).stdout.strip().split(',')
+            out = {'sm_mhz': float(q[0]), 'sm_max_mhz': float(q[1]), 'reasons': [], 'samples': 1, 'note': 'single nvidia-smi query after the run'}
         except Exception:
-            self.proc.kill()
-        self.fh.close()
-        sm, mx, reasons = [], [], set()
-        for line in open(self.path):
-            p = [x.strip() for x in line.split(',')]
-            if len(p) < 9:
-                continue
-            try:
-                sm.append(float(p[1])); mx.append(float(p[2]))
-            except ValueError:
-                continue
-            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), p[5:9]):
-                if val.lower().startswith('active'):
-                    reasons.add(name)
-        if sm:
-            out = {'sm_mhz': float(np.median(sm)), 'sm_max_mhz': float(max(mx)), 'reasons': sorted(reasons),
-                   'samples': len(sm)}
-        try:
-            os.remove(self.path)
-        except OSError:
             pass
         return out
 
@@ -254,11 +282,13 @@ def main():
         sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    sampler.mark(0)
     ev0.record()
     for _ in range(args.steps):
         rows_dev, n_rows_dev = step()
     ev1.record()
     barrier()
+    sampler.mark(1)
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     prof = ctx.get_profile()
