@@ -92,6 +92,38 @@ def test_dense_field_vs_oracle():
     ctx.close()
 
 
+def test_baseline_cfg3_dense_2000_rods_full_frame():
+    """BASELINE.json configs[2]: 2,000 bacteria per frame at 1228x922 with the adaptive double threshold -- labelling,
+    geometry and the general (more than 128 live tracks) linker path at full size; ids bit-exact against the oracle."""
+    from ysmr_b200.api import Context
+    cfg = SceneConfig(n_frames=6, n_cells=2000, seed=31, margin=20.0)
+    grey = render_frames(make_scene(cfg))
+    rows, _ = oracle_rows(grey, ref_stages.DetectSettings())
+    ctx = Context(cfg.height, cfg.width, 1, 0, max_batch=8, max_blobs=4096, max_tracks=8192)
+    got = ctx.track_device(torch.from_numpy(grey).cuda(), 0, rows_capacity=6 * 8192)
+    assert len(got) > 6 * 1500
+    ref = rows[np.lexsort((rows[:, 0], rows[:, 1]))][:, [1, 0, 2, 3, 4, 5, 6]]
+    _check_against_csv(got, ref)
+    ctx.close()
+
+
+def test_baseline_cfg4_coccoid_dark_on_light_2048():
+    """BASELINE.json configs[3]: 2048x2048 frames, coccoid cells, dark on light (exercises the marker-image quirk of
+    SURVEY finding 8, the width without scalar-tail columns and the BGR path at the larger frame size)."""
+    from ysmr_b200.api import Context
+    cfg = SceneConfig(width=2048, height=2048, n_frames=5, n_cells=200, seed=41, margin=40.0, background=160.0, intensity=80.0,
+                      noise_sigma=1.5, semi_major=2.5, semi_minor=2.5)
+    grey = render_frames(make_scene(cfg))
+    st = ref_stages.DetectSettings(False, 5, 2.0)
+    rows, _ = oracle_rows(grey, st)
+    ctx = Context(2048, 2048, 3, 0, white_on_dark=False, offset=5, adt=2.0, max_batch=8, max_blobs=8192, max_tracks=8192,
+                  max_runs=65536)
+    got = ctx.track_device(torch.from_numpy(to_bgr(grey)).cuda(), 0, rows_capacity=5 * 8192)
+    ref = rows[np.lexsort((rows[:, 0], rows[:, 1]))][:, [1, 0, 2, 3, 4, 5, 6]]
+    _check_against_csv(got, ref)
+    ctx.close()
+
+
 def test_properties_at_baseline_size():
     """Size-independent properties on full 1228x922 frames: translation of the whole scene by whole pixels moves every
     rectangle by exactly that vector; detection is independent of batch composition; masks are polarity-symmetric."""

@@ -240,6 +240,9 @@ __device__ __forceinline__ uint32_t luma_dp(uint32_t px)        // px = B | G <<
 }
 
 constexpr int PB_WARPS = 4;
+#ifndef PB_MIN_CTAS
+#define PB_MIN_CTAS 10
+#endif
 constexpr int PB_COLS = 256;                      // columns per warp of K1a: 8 adjacent pixels per lane
 
 struct GreyRow {                                   // one row of a lane: 8 pixels + 2 side pixels as 16-bit lanes
@@ -345,7 +348,7 @@ __device__ __forceinline__ uint2 blur_row(const GreyRow &v)
 }
 
 template <int C, bool FAST>
-__global__ void __launch_bounds__(PB_WARPS * 32) blur_prepass_kernel(FrontParams p, int n_strips, int n_chunks, int rows_per_chunk)
+__global__ void __launch_bounds__(PB_WARPS * 32, PB_MIN_CTAS) blur_prepass_kernel(FrontParams p, int n_strips, int n_chunks, int rows_per_chunk)
 {
     const int lane = threadIdx.x & 31;
     const int64_t task = (int64_t)blockIdx.x * PB_WARPS + (threadIdx.x >> 5);
@@ -428,7 +431,13 @@ __global__ void __launch_bounds__(256) plane_margins_kernel(FrontParams p)
 //     d = sat((b + 1.5*2^23 - t) - R)          (1.0f iff b - rint(mean) > t ; both operands are integers < 2^24)
 // and the lane's byte = sum d_mask[k] 2^k + d_marker[k] 2^(4+k) accumulated onto 2^23 so that it is the low mantissa byte.
 // The 2 x 8 halo columns of a strip are converted by all 32 lanes at once for 8 rows every 8 steps.
-constexpr int GD_WARPS = 4;
+#ifndef GD_WARPS_N
+#define GD_WARPS_N 4
+#endif
+#ifndef GD_MIN_CTAS
+#define GD_MIN_CTAS 4
+#endif
+constexpr int GD_WARPS = GD_WARPS_N;
 constexpr int GD_RING = 8;
 constexpr int GD_ROWF = 144;                      // floats per ring slot: 8 halo | 128 | 8 halo
 constexpr float GD_MAGIC = 12582912.0f;           // 1.5 * 2^23
@@ -498,7 +507,7 @@ __device__ __forceinline__ uint32_t gd_decide(const float (&m)[4], const float4 
 // scalar-tail columns (the last w % 8 columns of the column filter and the last w % 4 of the row filter are not
 // FMA-contracted); launched separately for those strips only so that the common code stays small.
 template <bool TAIL>
-__global__ void __launch_bounds__(GD_WARPS * 32, 4) gauss_decide_kernel(FrontParams p, int first_strip, int n_strips, int n_chunks, int rows_per_chunk)
+__global__ void __launch_bounds__(GD_WARPS * 32, GD_MIN_CTAS) gauss_decide_kernel(FrontParams p, int first_strip, int n_strips, int n_chunks, int rows_per_chunk)
 {
     __shared__ __align__(16) float ring_all[GD_WARPS][GD_RING * GD_ROWF];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
