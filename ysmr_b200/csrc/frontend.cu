@@ -232,119 +232,144 @@ __device__ __forceinline__ float gauss_col(float c, float m1, float p1, float m2
 // Blurred plane of one frame: rows -5 .. h+4, `pitch` bytes each; pixel (x, y) at (y + 5) * pitch + 8 + x; columns -8..-1
 // and w..w+7 and the 5 rows above / below hold BORDER_REPLICATE copies (what cv2.adaptiveThreshold's Gaussian sees).
 // =====================================================================================================================
-__device__ __forceinline__ uint32_t luma_dp(uint32_t px)        // px = B | G << 8 | R << 16 (byte 3 ignored)
-{
-    // (3735 B + 19235 G + 9798 R + 16384) >> 15 with the weights split into high and low bytes: two byte dot products
-    constexpr uint32_t HI = 14u | (75u << 8) | (38u << 16), LO = 151u | (35u << 8) | (70u << 16);
-    return (__dp4a(px, HI, 0u) * 256u + __dp4a(px, LO, 16384u)) >> 15;
-}
-
 constexpr int PB_WARPS = 4;
 #ifndef PB_MIN_CTAS
 #define PB_MIN_CTAS 10
 #endif
 constexpr int PB_COLS = 256;                      // columns per warp of K1a: 8 adjacent pixels per lane
 
-struct GreyRow {                                   // one row of a lane: 8 pixels + 2 side pixels as 16-bit lanes
-    uint32_t p01, p23, p45, p67, side;
-};
+// Q15 luma g = (3735 B + 19235 G + 9798 R + 16384) >> 15 of a pixel whose three bytes sit anywhere in one or two words, as
+// two 16-bit x 8-bit dot products (dp2a) with the weights arranged for the byte position -- no byte shuffling.  All weights
+// and the rounding constant are DOUBLED, so the sum is 2 * (...) and g is exactly byte 2 of it: a later byte permute picks
+// it up for free instead of a shift per pixel.
+constexpr uint32_t LW_BG = 7470u | (38470u << 16), LW_R0 = 19596u, LW_0B = 7470u << 16, LW_GR = 38470u | (19596u << 16);
+__device__ __forceinline__ uint32_t lsum_b012(uint32_t v) { return __dp2a_hi(LW_R0, v, __dp2a_lo(LW_BG, v, 32768u)); }
+__device__ __forceinline__ uint32_t lsum_b123(uint32_t v) { return __dp2a_hi(LW_GR, v, __dp2a_lo(LW_0B, v, 32768u)); }
+__device__ __forceinline__ uint32_t lsum_b3_01(uint32_t v, uint32_t n) { return __dp2a_lo(LW_GR, n, __dp2a_hi(LW_0B, v, 32768u)); }
+__device__ __forceinline__ uint32_t lsum_b23_0(uint32_t v, uint32_t n) { return __dp2a_lo(LW_R0, n, __dp2a_hi(LW_BG, v, 32768u)); }
 
-// Q15 luma (3735 B + 19235 G + 9798 R + 16384) >> 15 of a pixel whose three bytes sit anywhere in one or two words: two
-// 16-bit x 8-bit dot products (dp2a) with the weights arranged for the byte position, no byte shuffling.
-constexpr uint32_t LW_BG = 3735u | (19235u << 16), LW_R0 = 9798u, LW_0B = 3735u << 16, LW_GR = 19235u | (9798u << 16);
-__device__ __forceinline__ uint32_t luma_b012(uint32_t v) { return __dp2a_hi(LW_R0, v, __dp2a_lo(LW_BG, v, 16384u)) >> 15; }
-__device__ __forceinline__ uint32_t luma_b123(uint32_t v) { return __dp2a_hi(LW_GR, v, __dp2a_lo(LW_0B, v, 16384u)) >> 15; }
-__device__ __forceinline__ uint32_t luma_b3_01(uint32_t v, uint32_t n) { return __dp2a_lo(LW_GR, n, __dp2a_hi(LW_0B, v, 16384u)) >> 15; }
-__device__ __forceinline__ uint32_t luma_b23_0(uint32_t v, uint32_t n) { return __dp2a_lo(LW_R0, n, __dp2a_hi(LW_BG, v, 16384u)) >> 15; }
-
-// four BGR pixels (12 bytes = words w0, w1, w2) -> two pairs of 16-bit lanes
-__device__ __forceinline__ void luma4(uint32_t w0, uint32_t w1, uint32_t w2, uint32_t &pa, uint32_t &pb)
+// four BGR pixels (12 bytes = words w0, w1, w2) -> one word of four grey bytes
+__device__ __forceinline__ uint32_t grey4_of_bgr(uint32_t w0, uint32_t w1, uint32_t w2)
 {
-    pa = luma_b012(w0) | (luma_b3_01(w0, w1) << 16);
-    pb = luma_b23_0(w1, w2) | (luma_b123(w2) << 16);
+    const uint32_t a = __byte_perm(lsum_b012(w0), lsum_b3_01(w0, w1), 0x0062);     // (g0, g1, -, -)
+    const uint32_t b = __byte_perm(lsum_b23_0(w1, w2), lsum_b123(w2), 0x0062);     // (g2, g3, -, -)
+    return __byte_perm(a, b, 0x5410);
 }
 
-// Per-lane constants of the FAST path (w % 4 == 0, 4-byte aligned frames): every load is a whole 32-bit word at an address
-// that is always inside the row (lanes at the image border re-load one of their own words and the REFLECT_101 value is
-// then taken from registers), so the row loop has no divergent branches.
+// One row of a lane before the blur: grey bytes of its 8 pixels (w0, w1) and the words holding the two side pixels.
+struct RowBytes {
+    uint32_t w0, w1, wl, wr;
+};
+
+// Per-lane constants (FAST path: w % 4 == 0 and 4-byte aligned frames).  Every load is a whole 32-bit word at an address that
+// is always inside the row, and REFLECT_101 at the image border as well as the position of the side pixels inside their
+// words are folded into four byte-permute selectors, so the row loop has no branches and no selects.
 struct LaneGeom {
-    int hi_off;        // word offset of pixels 4..7 (0 when the lane only has 4 valid pixels: w % 8 == 4, last lane)
-    int l_off, r_off;  // word offsets of the words holding pixel gx-1 / gx+8 (0 at the image border)
-    bool half, left_edge, right_edge;
+    int hi_off;                  // word offset of pixels 4..7 (0 when the lane only has 4 valid pixels: w % 8 == 4, last lane)
+    int l_off, r_off;            // word offsets of the words holding pixel gx-1 / gx+8 (0 at the image border)
+    uint32_t sel_a0, sel_b0, sel_b1;     // (g-1,g0,g1,g2) from (wl,w0) ; (g1,g2,g3,g4) from (w0,w1) ; (g5,g6,g7,g8) from (w1,wr)
 };
 
 template <int C>
 __device__ __forceinline__ LaneGeom lane_geom(int w, int gx)
 {
     LaneGeom g;
-    g.half = w - gx < 8;
-    g.left_edge = gx == 0;
-    g.right_edge = !g.half && gx + 8 >= w;
-    g.hi_off = g.half ? 0 : C;
-    g.l_off = g.left_edge ? 0 : -1;
-    g.r_off = (g.half || g.right_edge) ? 0 : 2 * C;
+    const bool half = w - gx < 8, left_edge = gx == 0, right_edge = !half && gx + 8 >= w;
+    g.hi_off = half ? 0 : C;
+    g.l_off = left_edge ? 0 : -1;
+    g.r_off = (half || right_edge) ? 0 : 2 * C;
+    // the left pixel is byte 3 of wl (C == 1: last byte of the previous word) or byte 2 (C == 3: the luma sum); at the left
+    // image border column -1 is column 1 (REFLECT_101) = byte 1 of w0
+    g.sel_a0 = left_edge ? 0x6545u : (C == 1 ? 0x6543u : 0x6542u);
+    g.sel_b0 = half ? 0x2321u : 0x4321u;                           // w % 8 == 4, last lane: column w is column w-2
+    // the right pixel is byte 0 of wr (C == 1) or byte 2 of the luma sum (C == 3); at the right border column w is w-2
+    g.sel_b1 = right_edge ? 0x2321u : (C == 1 ? 0x4321u : 0x6321u);
     return g;
 }
 
+// Raw words of one row of a lane.  Loading and converting are separate steps so that the loads issued in one iteration are
+// first touched in the next: a whole iteration of latency hiding per warp (the kernel is bound by bytes in flight).
 template <int C>
-__device__ __forceinline__ GreyRow load_row_fast(const uint8_t *rowp, const LaneGeom &lg)
+struct RawRow {
+    uint32_t w[C == 1 ? 4 : 8];                            // C == 1: w0, w1, wl, wr ; C == 3: 3 + 3 BGR words, left, right
+};
+
+template <int C>
+__device__ __forceinline__ RawRow<C> fetch_row_fast(const uint8_t *rowp, const LaneGeom &lg)
 {
     const uint32_t *q = reinterpret_cast<const uint32_t *>(rowp);
-    GreyRow g;
-    uint32_t l, r;
+    RawRow<C> r;
     if (C == 1) {
-        const uint32_t lo = __ldg(q), hi = __ldg(q + lg.hi_off);
-        l = __ldg(q + lg.l_off) >> 24; r = __ldg(q + lg.r_off) & 0xFFu;
-        g.p01 = __byte_perm(lo, 0, 0x4140); g.p23 = __byte_perm(lo, 0, 0x4342);
-        g.p45 = __byte_perm(hi, 0, 0x4140); g.p67 = __byte_perm(hi, 0, 0x4342);
+        r.w[0] = __ldg(q); r.w[1] = __ldg(q + lg.hi_off); r.w[2] = __ldg(q + lg.l_off); r.w[3] = __ldg(q + lg.r_off);
     } else {
         const uint32_t *qh = q + 3 * lg.hi_off / C;        // hi_off is 0 or C -> 0 or 3 words
-        const uint32_t a0 = __ldg(q), a1 = __ldg(q + 1), a2 = __ldg(q + 2);
-        const uint32_t b0 = __ldg(qh), b1 = __ldg(qh + 1), b2 = __ldg(qh + 2);
-        const uint32_t vl = __ldg(q + lg.l_off), vr = __ldg(q + 3 * lg.r_off / C);
-        luma4(a0, a1, a2, g.p01, g.p23);
-        luma4(b0, b1, b2, g.p45, g.p67);
-        l = luma_b123(vl); r = luma_b012(vr);
+        r.w[0] = __ldg(q); r.w[1] = __ldg(q + 1); r.w[2] = __ldg(q + 2);
+        r.w[3] = __ldg(qh); r.w[4] = __ldg(qh + 1); r.w[5] = __ldg(qh + 2);
+        r.w[6] = __ldg(q + lg.l_off); r.w[7] = __ldg(q + 3 * lg.r_off / C);
     }
-    if (lg.left_edge) l = g.p01 >> 16;                     // REFLECT_101: column -1 is column 1
-    if (lg.right_edge) r = g.p67 & 0xFFFFu;                // column w is column w-2 (w % 8 == 0)
-    if (lg.half) { g.p45 = g.p23 & 0xFFFFu; g.p67 = 0; }  // column w is column w-2 (w % 8 == 4)
-    g.side = l | (r << 16);
-    return g;
+    return r;
 }
 
-// generic path: per-pixel loads with REFLECT_101 (any width / alignment, slow)
 template <int C>
-__device__ __forceinline__ GreyRow load_row_generic(const uint8_t *frame, int w, int y, int gx)
+__device__ __forceinline__ RowBytes bytes_of_raw(const RawRow<C> &x)
 {
-    GreyRow g;
+    RowBytes r;
+    if (C == 1) {
+        r.w0 = x.w[0]; r.w1 = x.w[1]; r.wl = x.w[2]; r.wr = x.w[3];
+    } else {
+        r.w0 = grey4_of_bgr(x.w[0], x.w[1], x.w[2]);
+        r.w1 = grey4_of_bgr(x.w[3], x.w[4], x.w[5]);
+        r.wl = lsum_b123(x.w[6]); r.wr = lsum_b012(x.w[7]);   // grey value in byte 2
+    }
+    return r;
+}
+
+// generic path: per-pixel loads with REFLECT_101 (any width / alignment, slow); same word layout as the FAST path
+template <int C>
+__device__ __forceinline__ RowBytes load_row_generic(const uint8_t *frame, int w, int y, int gx)
+{
     uint32_t v[10];
 #pragma unroll
     for (int k = 0; k < 10; ++k) v[k] = grey_px<C>(frame, w, y, reflect101(gx - 1 + k, w));
-    g.p01 = v[1] | (v[2] << 16); g.p23 = v[3] | (v[4] << 16); g.p45 = v[5] | (v[6] << 16); g.p67 = v[7] | (v[8] << 16);
-    g.side = v[0] | (v[9] << 16);
-    return g;
+    RowBytes r;
+    r.w0 = v[1] | (v[2] << 8) | (v[3] << 16) | (v[4] << 24);
+    r.w1 = v[5] | (v[6] << 8) | (v[7] << 16) | (v[8] << 24);
+    r.wl = C == 1 ? v[0] << 24 : v[0] << 16;
+    r.wr = C == 1 ? v[9] : v[9] << 16;
+    return r;
 }
 
-__device__ __forceinline__ GreyRow add_rows(const GreyRow &a, const GreyRow &b)
+// Horizontal 1-2-1 of one row as byte dot products: four packed pairs (h0,h1) .. (h6,h7), each value + 2 so that the
+// vertical 1-2-1 (weights sum to 4) carries the rounding constant 8 of (sum + 8) >> 4.
+struct HRow {
+    uint32_t h01, h23, h45, h67;
+};
+
+__device__ __forceinline__ HRow hblur(const RowBytes &r, const LaneGeom &lg)
 {
-    GreyRow s;
-    s.p01 = a.p01 + b.p01; s.p23 = a.p23 + b.p23; s.p45 = a.p45 + b.p45; s.p67 = a.p67 + b.p67; s.side = a.side + b.side;
+    const uint32_t a0 = __byte_perm(r.wl, r.w0, lg.sel_a0);       // (g-1, g0, g1, g2)
+    const uint32_t b0 = __byte_perm(r.w0, r.w1, lg.sel_b0);       // (g1, g2, g3, g4)
+    const uint32_t a1 = __byte_perm(r.w0, r.w1, 0x6543);          // (g3, g4, g5, g6)
+    const uint32_t b1 = __byte_perm(r.w1, r.wr, lg.sel_b1);       // (g5, g6, g7, g8)
+    constexpr uint32_t LO = 0x00010201u, HI = 0x01020100u;        // weights (1,2,1,0) and (0,1,2,1)
+    HRow h;
+    h.h01 = __dp4a(a0, LO, 2u) + (__dp4a(a0, HI, 2u) << 16);
+    h.h23 = __dp4a(b0, LO, 2u) + (__dp4a(b0, HI, 2u) << 16);
+    h.h45 = __dp4a(a1, LO, 2u) + (__dp4a(a1, HI, 2u) << 16);
+    h.h67 = __dp4a(b1, LO, 2u) + (__dp4a(b1, HI, 2u) << 16);
+    return h;
+}
+
+__device__ __forceinline__ HRow add_rows(const HRow &a, const HRow &b)
+{
+    HRow s;
+    s.h01 = a.h01 + b.h01; s.h23 = a.h23 + b.h23; s.h45 = a.h45 + b.h45; s.h67 = a.h67 + b.h67;
     return s;
 }
 
-__device__ __forceinline__ uint2 blur_row(const GreyRow &v)
+__device__ __forceinline__ uint2 blur_out(const HRow &v)          // v = h(y-1) + 2 h(y) + h(y+1) + 8 per 16-bit lane
 {
-    const uint32_t m0 = __byte_perm(v.side, v.p01, 0x5410);   // (v[-1], v0)
-    const uint32_t m1 = __byte_perm(v.p01, v.p23, 0x5432);    // (v1, v2)
-    const uint32_t m2 = __byte_perm(v.p23, v.p45, 0x5432);    // (v3, v4)
-    const uint32_t m3 = __byte_perm(v.p45, v.p67, 0x5432);    // (v5, v6)
-    const uint32_t m4 = __byte_perm(v.p67, v.side, 0x7632);   // (v7, v8)
-    const uint32_t o01 = (m0 + m1 + 0x00080008u + 2 * v.p01) >> 4;
-    const uint32_t o23 = (m1 + m2 + 0x00080008u + 2 * v.p23) >> 4;
-    const uint32_t o45 = (m2 + m3 + 0x00080008u + 2 * v.p45) >> 4;
-    const uint32_t o67 = (m3 + m4 + 0x00080008u + 2 * v.p67) >> 4;
-    return make_uint2(__byte_perm(o01, o23, 0x6420), __byte_perm(o45, o67, 0x6420));
+    return make_uint2(__byte_perm(v.h01 >> 4, v.h23 >> 4, 0x6420), __byte_perm(v.h45 >> 4, v.h67 >> 4, 0x6420));
 }
 
 template <int C, bool FAST>
@@ -366,24 +391,38 @@ __global__ void __launch_bounds__(PB_WARPS * 32, PB_MIN_CTAS) blur_prepass_kerne
     const int pitch = p.pitch;
     const int64_t stride = (int64_t)w * C;
     const uint8_t *col = frame + (int64_t)gx * C;                 // this lane's column in row 0
-    const LaneGeom lg = lane_geom<C>(w, gx);
-    auto row = [&](int y) -> GreyRow {                            // y already reflected into [0, h)
-        if (FAST) return load_row_fast<C>(col + y * stride, lg);
-        return load_row_generic<C>(frame, w, y, gx);
-    };
-    // rows y-1, y, y+1 slide through registers as S(y-1) = g(y-1) + g(y) and g(y); the row after next is in flight
-    GreyRow b = row(y0);
-    GreyRow s_prev = add_rows(row(reflect101(y0 - 1, h)), b);
-    GreyRow nxt = row(reflect101(y0 + 1, h));
+    LaneGeom lg = lane_geom<C>(w, gx);
+    if (!FAST) { lg.sel_a0 = C == 1 ? 0x6543u : 0x6542u; lg.sel_b0 = 0x4321u; lg.sel_b1 = C == 1 ? 0x4321u : 0x6321u; }   // borders done by the loads
+    // horizontal pass first (on bytes), then the vertical 1-2-1 slides through registers as S(y-1) = h(y-1) + h(y) and h(y)
+    if (FAST) {
+        auto fetch = [&](int y) { return fetch_row_fast<C>(col + y * stride, lg); };      // y already inside [0, h)
+        auto conv = [&](const RawRow<C> &x) { return hblur(bytes_of_raw<C>(x), lg); };
+        HRow b = conv(fetch(y0));
+        HRow s_prev = add_rows(conv(fetch(reflect101(y0 - 1, h))), b);
+        RawRow<C> raw = fetch(reflect101(y0 + 1, h));              // row y+1 of the first iteration, in flight
 #pragma unroll 2
-    for (int y = y0; y < y1; ++y) {
-        const GreyRow c = nxt;
-        int yn = y + 2; yn = yn >= h ? 2 * h - 2 - yn : yn;       // REFLECT_101 below the image (last chunk only)
-        if (y + 1 < y1) nxt = row(yn);                            // prefetch
-        const GreyRow s_cur = add_rows(b, c);                     // S(y) = g(y) + g(y+1)
-        *reinterpret_cast<uint2 *>(dst) = blur_row(add_rows(s_prev, s_cur));      // vertical 1-2-1, then horizontal
-        s_prev = s_cur; b = c;
-        dst += pitch;
+        for (int y = y0; y < y1; ++y) {
+            int yn = y + 2; yn = yn >= h ? 2 * h - 2 - yn : yn;   // REFLECT_101 below the image (last chunk only)
+            RawRow<C> ahead = raw;
+            if (y + 1 < y1) ahead = fetch(yn);                    // issue the loads of row y+2 ...
+            const HRow c = conv(raw);                             // ... and only now touch row y+1, loaded one iteration ago
+            raw = ahead;
+            const HRow s_cur = add_rows(b, c);                    // S(y) = h(y) + h(y+1)
+            *reinterpret_cast<uint2 *>(dst) = blur_out(add_rows(s_prev, s_cur));
+            s_prev = s_cur; b = c;
+            dst += pitch;
+        }
+    } else {
+        auto row = [&](int y) { return hblur(load_row_generic<C>(frame, w, y, gx), lg); };
+        HRow b = row(y0);
+        HRow s_prev = add_rows(row(reflect101(y0 - 1, h)), b);
+        for (int y = y0; y < y1; ++y) {
+            const HRow c = row(reflect101(y + 1, h));
+            const HRow s_cur = add_rows(b, c);
+            *reinterpret_cast<uint2 *>(dst) = blur_out(add_rows(s_prev, s_cur));
+            s_prev = s_cur; b = c;
+            dst += pitch;
+        }
     }
 }
 
