@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--batch', type=int, default=592, help='frames per detect launch')
     ap.add_argument('--cpu-frames', type=int, default=900, help='frames of the bounded CPU sample (about 15 s)')
     ap.add_argument('--e2e-frames', type=int, default=1000, help='frames in the pinned host buffer of the e2e leg')
+    ap.add_argument('--multi', default='stream', choices=['stream', 'gather'],
+                    help='N > 1: stream detection records chunk by chunk to the linker (default) or gather whole ranges')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
     return ap.parse_args()
@@ -207,14 +209,31 @@ def main():
     hbm_peak = float(peaks.get('hbm_gbs', 6650.0))
     peak_src = 'measured (MEASURED_PEAKS.json)' if 'hbm_gbs' in peaks else 'fallback 6.65 TB/s (B200_PROFILING.md)'
 
-    # ---- synthetic video of world*F frames; this rank renders and keeps frames [rank*F, (rank+1)*F) in HBM ------------
+    # ---- synthetic video of world*F frames.  N == 1 or --multi gather: this rank keeps the contiguous range
+    # [rank*F, (rank+1)*F).  --multi stream (default for N > 1): the video is cut into chunks of `batch` frames and chunk c
+    # belongs to rank c % N (frame-range sharding at chunk granularity), so that the one sequential linker on rank 0 can
+    # consume chunks in frame order while all ranks are still detecting.  Every rank holds ~F frames either way.
     scene = scene_for(args, world * F)
-    shape = (F, H, W) if Cn == 1 else (F, H, W, 3)
+    stream_mode = world > 1 and args.multi == 'stream'
+    B = args.batch
+    if stream_mode:
+        n_chunks = (world * F + B - 1) // B
+        chunk_range = lambda c: (c * B, min(world * F, (c + 1) * B))
+        my_chunks = [c for c in range(n_chunks) if c % world == rank]
+        spans = [chunk_range(c) for c in my_chunks]
+    else:
+        spans = [(rank * F, (rank + 1) * F)]
+    n_local = sum(b - a for a, b in spans)
+    shape = (n_local, H, W) if Cn == 1 else (n_local, H, W, 3)
     frames = torch.empty(shape, dtype=torch.uint8, device=dev)
     G = 200
-    for a in range(0, F, G):
-        b = min(F, a + G)
-        render_frames_torch(scene, rank * F + a, rank * F + b, dev, channels=Cn, out=frames[a:b])
+    pos, span_pos = 0, []
+    for a, b in spans:
+        span_pos.append(pos)
+        for x in range(a, b, G):
+            y = min(b, x + G)
+            render_frames_torch(scene, x, y, dev, channels=Cn, out=frames[pos:pos + (y - x)])
+            pos += y - x
     torch.cuda.synchronize()
 
     MB, MT = 128, 1024              # capacities: detections per frame (the scene has ~50), live tracks
@@ -265,7 +284,70 @@ def main():
             total += nr
         return rows_buf, total
 
-    step = step_single if world == 1 else step_multi
+    # streamed hand-over: one byte buffer per chunk = int32 counts[nf] followed by float32 blobs[nf][MB][5]
+    if stream_mode:
+        rec_bytes = 4 + MB * 5 * 4
+
+        def chunk_views(buf, nf):
+            counts = buf[:nf * 4].view(torch.int32)
+            blobs = buf[nf * 4:nf * rec_bytes].view(torch.float32).view(nf, MB, 5)
+            return counts, blobs
+
+        chunk_buf = {}
+        if rank == 0:
+            for c in range(n_chunks):
+                a, b = chunk_range(c)
+                chunk_buf[c] = torch.empty(((b - a) * rec_bytes + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+        else:
+            for c in my_chunks:
+                a, b = chunk_range(c)
+                chunk_buf[c] = torch.empty(((b - a) * rec_bytes + 15) // 16 * 16, dtype=torch.uint8, device=dev)
+        # the serial linker goes first whenever it is ready: highest stream priority, like the library's own pipeline
+        det_stream, link_stream = torch.cuda.Stream(dev), torch.cuda.Stream(dev, priority=-1)
+        n_rows_run = torch.zeros(1, dtype=torch.int64, device=dev)
+
+        def detect_chunk(i, c, stream):
+            a, b = chunk_range(c)
+            counts, blobs = chunk_views(chunk_buf[c], b - a)
+            fr = frames[span_pos[i]:span_pos[i] + (b - a)]
+            ctx._check(ctx.lib.ysmr_detect(ctx._h, C.c_void_p(fr.data_ptr()), b - a, int(np.prod(shape[1:])), a,
+                                           C.c_void_p(counts.data_ptr()), C.c_void_p(blobs.data_ptr()), None,
+                                           C.c_void_p(stream.cuda_stream)))
+
+        def step_stream():
+            cur = torch.cuda.current_stream(dev)
+            if rank != 0:
+                reqs = []
+                for i, c in enumerate(my_chunks):
+                    detect_chunk(i, c, cur)
+                    reqs.append(dist.isend(chunk_buf[c], dst=0))
+                for r in reqs:
+                    r.wait()
+                return None, None
+            ctx.reset()
+            n_rows_run.zero_()
+            det_stream.wait_stream(cur); link_stream.wait_stream(cur)
+            reqs = {c: dist.irecv(chunk_buf[c], src=c % world) for c in range(n_chunks) if c % world != 0}
+            done = {}
+            with torch.cuda.stream(det_stream):
+                for i, c in enumerate(my_chunks):
+                    detect_chunk(i, c, det_stream)
+                    done[c] = det_stream.record_event()
+            with torch.cuda.stream(link_stream):
+                for c in range(n_chunks):
+                    a, b = chunk_range(c)
+                    if c in done:
+                        link_stream.wait_event(done[c])
+                    else:
+                        reqs[c].wait()                     # NCCL: makes the current (link) stream wait, not the host
+                    counts, blobs = chunk_views(chunk_buf[c], b - a)
+                    ctx._check(ctx.lib.ysmr_link_append(ctx._h, C.c_void_p(counts.data_ptr()), C.c_void_p(blobs.data_ptr()), a, b - a,
+                                                        C.c_void_p(rows_buf.data_ptr()), rows_cap, C.c_void_p(n_rows_run.data_ptr()),
+                                                        C.c_void_p(link_stream.cuda_stream)))
+            cur.wait_stream(link_stream); cur.wait_stream(det_stream)
+            return rows_buf, n_rows_run
+
+    step = step_single if world == 1 else (step_stream if stream_mode else step_multi)
 
     def barrier():
         if world > 1:
@@ -316,7 +398,7 @@ def main():
     # ncu capture (profiles/r1_traffic.json) when present.
     fe_ms, fe_n = prof['frontend']
     bytes_per_frame = H * W * Cn
-    frames_per_launch = (F * args.steps) / max(fe_n, 1)
+    frames_per_launch = (n_local * args.steps) / max(fe_n, 1)
     per_launch_ms = fe_ms / max(fe_n, 1)
     achieved = (bytes_per_frame * frames_per_launch) / (per_launch_ms / 1000.0) / 1e9 if fe_ms > 0 else 0.0
     traffic = None
@@ -382,7 +464,10 @@ def main():
         'config': {'workload': f'cfg2: 1228x922x{Cn} (BGR as cap.read() delivers) x {F} frames per GPU, {args.cells} rods, '
                                f'default tracking.ini (white-on-dark, offset 5, adaptive double threshold 2.0, gsff 10/20/30)',
                    'frames_per_gpu': F, 'batch': args.batch, 'l2': 'inputs (>= 10 GB) far exceed the 126 MB L2',
-                   'parallelism': f'frame-range x{world}, one sequential linker', 'rows': n_rows, 'tracks': n_tracks,
+                   'parallelism': (f'frame-range x{world}, one sequential linker' if not stream_mode else
+                                   f'chunk-interleaved frame ranges x{world} ({B}-frame chunks, chunk c on rank c % {world}), '
+                                   f'records streamed over NCCL to the one sequential linker on rank 0'),
+                   'rows': n_rows, 'tracks': n_tracks,
                    'max_blobs': MB, 'max_tracks': MT},
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
     }

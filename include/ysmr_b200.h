@@ -129,6 +129,10 @@ int ysmr_detect(ysmr_ctx *ctx, const uint8_t *d_frames, int n_frames, int64_t fr
  *   d_n_rows                 [1] number of rows written by THIS call */
 int ysmr_link(ysmr_ctx *ctx, const int32_t *d_blob_count, const float *d_blobs, int first_frame, int n_frames,
               ysmr_row *d_rows, int64_t rows_capacity, int64_t *d_n_rows, void *stream);
+/* Same, appending: rows are written from d_rows[*d_n_rows] on and *d_n_rows (device, in/out) becomes the running total, so
+ * chunk after chunk can be enqueued without a host round trip (streamed multi-GPU hand-over, bench.py). */
+int ysmr_link_append(ysmr_ctx *ctx, const int32_t *d_blob_count, const float *d_blobs, int first_frame, int n_frames,
+                     ysmr_row *d_rows, int64_t rows_capacity, int64_t *d_n_rows, void *stream);
 int ysmr_link_reset(ysmr_ctx *ctx);                    /* forget all tracks, next id = 0 (new video) */
 
 /* Snapshot of the linker (for tests and for hand-over between processes).  Synchronous.

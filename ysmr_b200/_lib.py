@@ -57,6 +57,8 @@ EXPORTS = {
                               C.POINTER(DebugOut), C.c_void_p]),
     'ysmr_link': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
                             C.c_void_p]),
+    'ysmr_link_append': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int64, C.c_void_p,
+                                   C.c_void_p]),
     'ysmr_link_reset': (C.c_int, [C.c_void_p]),
     'ysmr_link_state_export': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_size_t)]),
     'ysmr_link_state_import': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),

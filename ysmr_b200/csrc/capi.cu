@@ -476,6 +476,17 @@ int ysmr_link(ysmr_ctx *c, const int32_t *d_blob_count, const float *d_blobs, in
     return link_impl(c, d_blob_count, d_blobs, first_frame, n_frames, d_rows, rows_capacity, d_n_rows, 0, (cudaStream_t)stream);
 }
 
+int ysmr_link_append(ysmr_ctx *c, const int32_t *d_blob_count, const float *d_blobs, int first_frame, int n_frames,
+                     ysmr_row *d_rows, int64_t rows_capacity, int64_t *d_n_rows, void *stream)
+{
+    if (!c || !d_blob_count || !d_blobs || !d_rows || !d_n_rows) return fail(c, YSMR_E_INVALID, "null argument");
+    if (n_frames < 0) return fail(c, YSMR_E_INVALID, "negative n_frames");
+    int r = link_ready(c);
+    if (r) return r;
+    CU(c, cudaSetDevice(c->device));
+    return link_impl(c, d_blob_count, d_blobs, first_frame, n_frames, d_rows, rows_capacity, d_n_rows, 1, (cudaStream_t)stream);
+}
+
 int ysmr_link_reset(ysmr_ctx *c)
 {
     if (!c) return YSMR_E_INVALID;

@@ -138,7 +138,7 @@ def render_frames_torch(scene: Scene, start: int, stop: int, device, channels: i
     cfg = scene.cfg
     n = stop - start
     dev = torch.device(device)
-    g = torch.Generator(device=dev); g.manual_seed(cfg.seed * 1000003 + start)
+    g = torch.Generator(device=dev)
     img = torch.full((n, cfg.height, cfg.width), float(cfg.background), device=dev, dtype=torch.float32)
     alpha, x0, y0 = [], [], []
     for t in range(start, stop):
@@ -154,7 +154,9 @@ def render_frames_torch(scene: Scene, start: int, stop: int, device, channels: i
     flat = (ff * cfg.height + yy) * cfg.width + xx
     val = cfg.background + amp * alpha
     img.view(-1).scatter_reduce_(0, flat.reshape(-1), val.reshape(-1), reduce='amax' if amp > 0 else 'amin')
-    img += torch.randn(img.shape, generator=g, device=dev, dtype=torch.float32) * cfg.noise_sigma
+    for i in range(n):                      # one noise stream per FRAME, so the bytes do not depend on how the caller batches
+        g.manual_seed(cfg.seed * 1000003 + start + i)
+        img[i] += torch.randn(img.shape[1:], generator=g, device=dev, dtype=torch.float32) * cfg.noise_sigma
     grey = img.round_().clamp_(0, 255).to(torch.uint8)
     if channels == 1:
         if out is not None:
