@@ -78,6 +78,41 @@ def _worker(rank, world, port, mode, out_path):
     dist.destroy_process_group()
 
 
+def _worker_streamed(rank, world, port, mode, out_path):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    from ysmr_b200.shard import track_streamed
+    grey = _frames()
+    lead = 10 if mode == 'meanstd' else 0
+    linker = _OracleLinker()
+    rows = track_streamed(len(grey), 7, world, rank, lambda a, b: _oracle_detect(grey, mode, a, b), linker, lead_in=lead,
+                          dist=dist, device=torch.device('cpu'), max_blobs=64)
+    if rank == 0:
+        np.save(out_path, np.concatenate(rows))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize('world,mode', [(2, 'adaptive'), (3, 'adaptive'), (2, 'meanstd')])
+def test_streamed_chunks_equal_single_process(tmp_path, world, mode):
+    """chunk-interleaved sharding (chunk c on rank c % world, 7-frame chunks, last one ragged) with the streamed hand-over"""
+    out = str(tmp_path / 'rows.npy')
+    mp.spawn(_worker_streamed, args=(world, _free_port(), mode, out), nprocs=world, join=True)
+    got = np.load(out)
+    grey = _frames()
+    c, b = _oracle_detect(grey, mode, 0, len(grey))
+    ref = _OracleLinker()(c, b, 0)
+    assert got.shape == ref.shape and (got == ref).all()
+
+
+def test_chunk_spans_and_owner():
+    from ysmr_b200.shard import chunk_owner, chunk_spans
+    sp = chunk_spans(45, 7)
+    assert sp[0] == (0, 7) and sp[-1] == (42, 45) and all(a[1] == b[0] for a, b in zip(sp, sp[1:]))
+    assert [chunk_owner(c, 3) for c in range(7)] == [0, 1, 2, 0, 1, 2, 0]
+    assert chunk_spans(0, 7) == []
+
+
 @pytest.mark.parametrize('world,mode', [(2, 'adaptive'), (3, 'adaptive'), (2, 'meanstd')])
 def test_sharded_equals_single_process(tmp_path, world, mode):
     out = str(tmp_path / 'rows.npy')

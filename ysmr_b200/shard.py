@@ -14,7 +14,7 @@ from __future__ import annotations
 
 import numpy as np
 
-__all__ = ['frame_ranges', 'read_range', 'gather_detections', 'track_sharded']
+__all__ = ['frame_ranges', 'read_range', 'gather_detections', 'track_sharded', 'chunk_owner', 'chunk_spans', 'track_streamed']
 
 
 def frame_ranges(n_frames: int, world: int):
@@ -85,4 +85,73 @@ def track_sharded(n_frames, world, rank, detect_range, link_range, lead_in=0, di
         rows.append(link_range(c, b, first))
         first += int(c.numel())
     assert first == n_frames
+    return rows
+
+
+# ---- chunk-interleaved sharding with a streamed hand-over --------------------------------------------------------------------
+# Contiguous ranges make the one sequential linker wait for whole ranges.  Cutting the video into chunks of `chunk` frames and
+# giving chunk c to rank c % world lets the linker (rank 0) consume chunks in frame order while every rank is still detecting:
+# the job then runs at max(detection / world, linking) instead of detection + (world - 1) * linking.  Still frame-range
+# sharding, still one linker, results identical to the single-GPU run.
+
+def chunk_spans(n_frames: int, chunk: int):
+    """[(start, stop)] of the chunks of a video, in frame order."""
+    return [(a, min(n_frames, a + chunk)) for a in range(0, n_frames, chunk)]
+
+
+def chunk_owner(c: int, world: int) -> int:
+    return c % world
+
+
+def track_streamed(n_frames, chunk, world, rank, detect_range, link_range, lead_in=0, dist=None, device=None, max_blobs=None):
+    """detect_range(read_start, stop) -> (counts int32 [n], blobs float32 [n, max_blobs, 5]) for frames [read_start, stop);
+    link_range(counts, blobs, first_frame) -> rows, called on rank 0 once per chunk in frame order.  Chunks detected by other
+    ranks travel to rank 0 as one point-to-point message each (counts packed in front of the blobs as float32).  `lead_in`
+    frames before a chunk are detected and dropped (mean/std mode).  Returns the list of row arrays on rank 0, else None."""
+    import torch
+    spans = chunk_spans(n_frames, chunk)
+    rows = []
+    if world == 1:
+        for a, b in spans:
+            rs, dropped = read_range(a, b, lead_in)
+            c, bl = detect_range(rs, b)
+            rows.append(link_range(c[dropped:], bl[dropped:], a))
+        return rows
+
+    def pack(c, bl):
+        return torch.cat([c.to(torch.float32).reshape(-1, 1), bl.reshape(bl.shape[0], -1)], 1).contiguous()
+
+    def unpack(buf, k):
+        return buf[:, 0].to(torch.int32).contiguous(), buf[:, 1:].reshape(buf.shape[0], k, 5).contiguous()
+
+    if rank != 0:
+        reqs, keep = [], []
+        for ci, (a, b) in enumerate(spans):
+            if chunk_owner(ci, world) != rank:
+                continue
+            rs, dropped = read_range(a, b, lead_in)
+            c, bl = detect_range(rs, b)
+            buf = pack(c[dropped:], bl[dropped:])
+            keep.append(buf)                           # must stay alive until the send has completed
+            reqs.append(dist.isend(buf, dst=0))
+        for r in reqs:
+            r.wait()
+        return None
+    assert max_blobs is not None, 'rank 0 needs the record width to post its receives'
+    pending = {}
+    for ci, (a, b) in enumerate(spans):                # post every receive up front, in frame order per source
+        o = chunk_owner(ci, world)
+        if o != 0:
+            buf = torch.empty((b - a, 1 + max_blobs * 5), dtype=torch.float32, device=device)
+            pending[ci] = (buf, dist.irecv(buf, src=o))
+    for ci, (a, b) in enumerate(spans):
+        if ci in pending:
+            buf, req = pending.pop(ci)
+            req.wait()
+            c, bl = unpack(buf, max_blobs)
+        else:
+            rs, dropped = read_range(a, b, lead_in)
+            c, bl = detect_range(rs, b)
+            c, bl = c[dropped:], bl[dropped:]
+        rows.append(link_range(c, bl, a))
     return rows
