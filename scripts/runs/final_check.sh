@@ -1,0 +1,5 @@
+set -x
+timeout 1200 python -m pytest tests -m gpu -x -q > gpurun_out/t_final.log 2>&1; echo "pytest rc=$?" >> gpurun_out/t_final.log
+( time python bench.py ) > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
+( time python bench.py --impl reference ) > gpurun_out/bench_reference.json 2> gpurun_out/bench_reference.err
+python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1
