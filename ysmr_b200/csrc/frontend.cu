@@ -434,27 +434,41 @@ __global__ void __launch_bounds__(256) plane_margins_kernel(FrontParams p)
     const int wpr = p.pitch / 4;                                  // words per plane row
     const int64_t per_frame = (int64_t)p.h + 10 * (int64_t)wpr;
     const int64_t total = per_frame * p.n_frames;
+    const bool w4 = (p.w & 3) == 0;
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int f = (int)(i / per_frame);
-        const int64_t k = i - (int64_t)f * per_frame;
+        const int k = (int)(i - (int64_t)f * per_frame);
         uint8_t *plane = p.plane + (int64_t)f * p.plane_stride;
         if (k < p.h) {
             uint8_t *row = plane + (k + 5) * (int64_t)p.pitch + 8;
-            const uint32_t l = row[0] * 0x01010101u, r = row[p.w - 1] * 0x01010101u;
-            reinterpret_cast<uint32_t *>(row)[-2] = l; reinterpret_cast<uint32_t *>(row)[-1] = l;
-            for (int x = p.w; x < p.w + 8; ++x) row[x] = (uint8_t)r;
+            uint32_t *row32 = reinterpret_cast<uint32_t *>(row);
+            const uint32_t l = (row32[0] & 0xFFu) * 0x01010101u;
+            row32[-2] = l; row32[-1] = l;
+            if (w4) {
+                const uint32_t r = (row32[p.w / 4 - 1] >> 24) * 0x01010101u;
+                row32[p.w / 4] = r; row32[p.w / 4 + 1] = r;
+            } else {
+                const uint8_t r = row[p.w - 1];
+                for (int x = p.w; x < p.w + 8; ++x) row[x] = r;
+            }
         } else {
-            const int64_t kk = k - p.h;
-            const int mr = (int)(kk / wpr), word = (int)(kk - (int64_t)mr * wpr);
+            const int kk = k - p.h;
+            const int mr = kk / wpr, word = kk - mr * wpr;
             const int dst_row = mr < 5 ? mr : p.h + 5 + (mr - 5);              // plane row index (image row + 5)
             const int src_row = mr < 5 ? 5 : p.h + 4;
             const uint8_t *src = plane + (int64_t)src_row * p.pitch + 8;
-            uint32_t v = 0;
+            const int x0 = 4 * word - 8;
+            uint32_t v;
+            if (x0 >= 0 && x0 + 3 < p.w) {
+                v = *reinterpret_cast<const uint32_t *>(src + x0);             // interior word: copy as is
+            } else {
+                v = 0;
 #pragma unroll
-            for (int b = 0; b < 4; ++b) {
-                int x = 4 * word + b - 8;
-                x = x < 0 ? 0 : (x >= p.w ? p.w - 1 : x);
-                v |= (uint32_t)src[x] << (8 * b);
+                for (int b = 0; b < 4; ++b) {
+                    int x = x0 + b;
+                    x = x < 0 ? 0 : (x >= p.w ? p.w - 1 : x);
+                    v |= (uint32_t)src[x] << (8 * b);
+                }
             }
             reinterpret_cast<uint32_t *>(plane + (int64_t)dst_row * p.pitch)[word] = v;
         }
@@ -655,20 +669,27 @@ __device__ __forceinline__ uint32_t squeeze_nibbles(uint32_t v)   // nibbles at 
 
 __global__ void __launch_bounds__(256) pack_masks_kernel(FrontParams p)
 {
-    // grid = (words of a frame / 256, frames): 32-bit index arithmetic only
+    // grid = (word pairs of a frame / 256, frames): 32-bit index arithmetic only; one thread packs two adjacent words of a
+    // row from 16 decision bytes (dec_pitch is a multiple of 32, so the 16-byte load is aligned and inside the row)
     const int ww = p.ww, f = blockIdx.y;
+    const int pairs = (ww + 1) >> 1;
     const uint32_t i = blockIdx.x * 256u + threadIdx.x;
-    if (i >= (uint32_t)(p.h * ww)) return;
-    const uint32_t y = i / (uint32_t)ww, word = i - y * (uint32_t)ww;
+    if (i >= (uint32_t)(p.h * pairs)) return;
+    const uint32_t y = i / (uint32_t)pairs, word = 2u * (i - y * (uint32_t)pairs);
     const uint32_t inv = p.inverted ? 0xFFFFFFFFu : 0u;
-    const uint2 d = *reinterpret_cast<const uint2 *>(p.decisions + (int64_t)f * p.dec_stride + (int64_t)y * p.dec_pitch + 8 * word);
-    const uint32_t mask = squeeze_nibbles(d.x & 0x0F0F0F0Fu) | (squeeze_nibbles(d.y & 0x0F0F0F0Fu) << 16);
-    const uint32_t mark = squeeze_nibbles((d.x >> 4) & 0x0F0F0F0Fu) | (squeeze_nibbles((d.y >> 4) & 0x0F0F0F0Fu) << 16);
-    const int left = p.w - 32 * (int)word;
-    const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
-    const int64_t o = (int64_t)f * p.h * ww + i;
-    p.mask_bits[o] = (mask ^ inv) & valid;
-    if (p.marker_bits) p.marker_bits[o] = (mark ^ inv) & valid;
+    const uint4 d = *reinterpret_cast<const uint4 *>(p.decisions + (int64_t)f * p.dec_stride + (int64_t)y * p.dec_pitch + 8 * word);
+    const uint32_t lo[2] = {d.x, d.z}, hi[2] = {d.y, d.w};
+    const int64_t o = ((int64_t)f * p.h + y) * ww + word;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        if ((int)word + k >= ww) break;
+        const uint32_t mask = squeeze_nibbles(lo[k] & 0x0F0F0F0Fu) | (squeeze_nibbles(hi[k] & 0x0F0F0F0Fu) << 16);
+        const uint32_t mark = squeeze_nibbles((lo[k] >> 4) & 0x0F0F0F0Fu) | (squeeze_nibbles((hi[k] >> 4) & 0x0F0F0F0Fu) << 16);
+        const int left = p.w - 32 * ((int)word + k);
+        const uint32_t valid = left >= 32 ? 0xFFFFFFFFu : ((1u << left) - 1u);
+        p.mask_bits[o + k] = (mask ^ inv) & valid;
+        if (p.marker_bits) p.marker_bits[o + k] = (mark ^ inv) & valid;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -840,7 +861,7 @@ cudaError_t launch_gauss_decide(const FrontParams &p, cudaStream_t st, cudaStrea
 // K1c (1 launch)
 cudaError_t launch_pack_masks(const FrontParams &p, cudaStream_t st)
 {
-    pack_masks_kernel<<<dim3((unsigned)((p.h * p.ww + 255) / 256), (unsigned)p.n_frames), 256, 0, st>>>(p);
+    pack_masks_kernel<<<dim3((unsigned)((p.h * ((p.ww + 1) / 2) + 255) / 256), (unsigned)p.n_frames), 256, 0, st>>>(p);
     return cudaGetLastError();
 }
 
