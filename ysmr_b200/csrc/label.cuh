@@ -75,11 +75,22 @@ YSMR_HD int popc32(uint32_t v)
 #endif
 }
 
-// number of runs that START in this row
+// number of runs that START in this row.  Words are fetched four at a time (independent loads in flight; the masks are
+// sparse, so an all-zero group is skipped with one test).
 YSMR_HD uint32_t count_row_runs(const uint32_t *row, int ww)
 {
     uint32_t n = 0, carry = 0;
-    for (int i = 0; i < ww; ++i) {
+    int i = 0;
+    for (; i + 4 <= ww; i += 4) {
+        const uint32_t b0 = row[i], b1 = row[i + 1], b2 = row[i + 2], b3 = row[i + 3];
+        if ((b0 | b1 | b2 | b3) == 0u) { carry = 0; continue; }
+        n += popc32(b0 & ~((b0 << 1) | carry));
+        n += popc32(b1 & ~((b1 << 1) | (b0 >> 31)));
+        n += popc32(b2 & ~((b2 << 1) | (b1 >> 31)));
+        n += popc32(b3 & ~((b3 << 1) | (b2 >> 31)));
+        carry = b3 >> 31;
+    }
+    for (; i < ww; ++i) {
         const uint32_t b = row[i];
         n += popc32(b & ~((b << 1) | carry));
         carry = b >> 31;
@@ -87,33 +98,45 @@ YSMR_HD uint32_t count_row_runs(const uint32_t *row, int ww)
     return n;
 }
 
+// runs of one word appended at index k (continuing a run that is open from the previous word)
+YSMR_HD void write_word_runs(uint32_t b, int base, int y, uint32_t &k, bool &open, uint32_t cap, uint16_t *x0s, uint16_t *x1s,
+                             uint16_t *ys)
+{
+    if (open) {
+        if (b == 0xFFFFFFFFu) return;
+        const int z = ctz32(~b);                           // first zero bit closes the run
+        if (k < cap) x1s[k] = (uint16_t)(base + z - 1);
+        ++k;
+        open = false;
+        b &= ~((1u << z) - 1u);
+    }
+    while (b) {
+        const int s = ctz32(b);
+        const uint32_t t = ~(b >> s);                      // zeros of the shifted word; bits above 31-s are 1
+        if (k < cap) { x0s[k] = (uint16_t)(base + s); ys[k] = (uint16_t)y; }
+        const int len = t ? ctz32(t) : 32;
+        if (s + len >= 32) { open = true; break; }         // runs to the end of this word
+        if (k < cap) x1s[k] = (uint16_t)(base + s + len - 1);
+        ++k;
+        b &= ~(((1u << len) - 1u) << s);
+    }
+}
+
 // write the runs of one row at index k.., returns the next free index.  Writes nothing at or beyond cap.
 YSMR_HD uint32_t write_row_runs(const uint32_t *row, int ww, int w, int y, uint32_t k, uint32_t cap, uint16_t *x0s,
                                 uint16_t *x1s, uint16_t *ys)
 {
     bool open = false;
-    for (int i = 0; i < ww; ++i) {
-        uint32_t b = row[i];
-        const int base = i << 5;
-        if (open) {
-            if (b == 0xFFFFFFFFu) continue;
-            const int z = ctz32(~b);                       // first zero bit closes the run
-            if (k < cap) x1s[k] = (uint16_t)(base + z - 1);
-            ++k;
-            open = false;
-            b &= ~((1u << z) - 1u);
-        }
-        while (b) {
-            const int s = ctz32(b);
-            const uint32_t t = ~(b >> s);                  // zeros of the shifted word; bits above 31-s are 1
-            if (k < cap) { x0s[k] = (uint16_t)(base + s); ys[k] = (uint16_t)y; }
-            const int len = t ? ctz32(t) : 32;
-            if (s + len >= 32) { open = true; break; }     // runs to the end of this word
-            if (k < cap) x1s[k] = (uint16_t)(base + s + len - 1);
-            ++k;
-            b &= ~(((1u << len) - 1u) << s);
-        }
+    int i = 0;
+    for (; i + 4 <= ww; i += 4) {
+        const uint32_t b0 = row[i], b1 = row[i + 1], b2 = row[i + 2], b3 = row[i + 3];
+        if (!open && (b0 | b1 | b2 | b3) == 0u) continue;
+        write_word_runs(b0, i << 5, y, k, open, cap, x0s, x1s, ys);
+        write_word_runs(b1, (i + 1) << 5, y, k, open, cap, x0s, x1s, ys);
+        write_word_runs(b2, (i + 2) << 5, y, k, open, cap, x0s, x1s, ys);
+        write_word_runs(b3, (i + 3) << 5, y, k, open, cap, x0s, x1s, ys);
     }
+    for (; i < ww; ++i) write_word_runs(row[i], i << 5, y, k, open, cap, x0s, x1s, ys);
     if (open) {
         if (k < cap) x1s[k] = (uint16_t)(w - 1);
         ++k;
