@@ -69,6 +69,7 @@ struct HostCta {
     int tid() const { return 0; }
     int nthr() const { return 1; }
     void sync() const {}
+    void relocate(ysmr::LabelFrame &, uint32_t) const {}
     uint32_t exclusive_scan(uint32_t *a, int n) const
     {
         uint32_t s = 0;

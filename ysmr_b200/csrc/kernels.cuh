@@ -21,6 +21,7 @@ struct LabelLaunch {
     uint32_t *work;              // [n_frames * max_blobs] compact (frame << 16 | blob) list for the geometry kernel
     uint32_t *work_count;        // [1]
     int32_t *status, *first_bad; // [1] each
+    int fast_runs;               // set by launch_label: runs per frame whose union-find arrays fit shared memory
 };
 
 struct GeoLaunch {

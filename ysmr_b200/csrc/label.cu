@@ -12,6 +12,20 @@ namespace ysmr {
 // ---- CTA policy for label_frame ------------------------------------------------------------------------------------
 struct DevCta {
     uint32_t *warp_sums;   // shared, [33]
+    uint32_t *fast;        // dynamic shared memory: parent, seed, kparent [fast_runs each], ext [fast_runs + 1], gparent [fast_runs + h + 2]
+    uint32_t fast_runs;
+    // Pointer chasing in parent[] / gparent[] dominates the later phases; in shared memory each hop costs ~30 cycles
+    // instead of an L2 round trip.  Frames with more runs than fit keep the global scratch.
+    __device__ void relocate(LabelFrame &f, uint32_t n_runs) const
+    {
+        if (n_runs > fast_runs) return;
+        uint32_t *q = fast;
+        f.parent = q; q += fast_runs;
+        f.seed = q; q += fast_runs;
+        f.kparent = q; q += fast_runs;
+        f.ext = q; q += fast_runs + 1;
+        f.gparent = q;
+    }
     __device__ int tid() const { return threadIdx.x; }
     __device__ int nthr() const { return blockDim.x; }
     __device__ void sync() const { __syncthreads(); }
@@ -61,7 +75,8 @@ struct DevCta {
 __global__ void __launch_bounds__(LABEL_THREADS, LABEL_MIN_CTAS) label_kernel(LabelLaunch L)
 {
     __shared__ uint32_t warp_sums[33];
-    DevCta cta{warp_sums};
+    extern __shared__ uint32_t fast_mem[];
+    DevCta cta{warp_sums, fast_mem, (uint32_t)L.fast_runs};
     const int slot = blockIdx.x;
     uint8_t *base = L.scratch + (size_t)slot * L.scratch_stride;
     for (int f = blockIdx.x; f < L.n_frames; f += gridDim.x) {
@@ -111,9 +126,22 @@ size_t label_scratch_bytes(int h, int max_runs)
     return 2 * al(4 * (size_t)(h + 1)) + 6 * al(2 * R) + 3 * al(4 * R) + al(4 * (R + 1)) + al(4 * (R + (size_t)h + 2));
 }
 
-cudaError_t launch_label(const LabelLaunch &L, int grid, cudaStream_t st)
+// Shared-memory budget per CTA for the union-find arrays: LABEL_MIN_CTAS CTAs of this size still fit one SM.
+constexpr size_t LABEL_FAST_BYTES = 45 * 1024;
+
+int label_fast_runs(int h)
 {
-    label_kernel<<<grid, LABEL_THREADS, 0, st>>>(L);
+    const long words = (long)(LABEL_FAST_BYTES / 4) - (long)h - 3;
+    const long r = words / 5;
+    return r >= 256 ? (int)r : 0;
+}
+
+cudaError_t launch_label(const LabelLaunch &L0, int grid, cudaStream_t st)
+{
+    LabelLaunch L = L0;
+    L.fast_runs = label_fast_runs(L.h);
+    const size_t smem = L.fast_runs ? 4 * ((size_t)5 * L.fast_runs + (size_t)L.h + 3) : 0;
+    label_kernel<<<grid, LABEL_THREADS, smem, st>>>(L);
     return cudaGetLastError();
 }
 

@@ -218,9 +218,10 @@ YSMR_HD void clear_bits(const Cta &cta, uint32_t *row, int x0, int x1)
 // ---- the per-frame program ---------------------------------------------------------------------------------------
 
 template <class Cta>
-YSMR_HD void label_frame(Cta &cta, const LabelFrame &f)
+YSMR_HD void label_frame(Cta &cta, const LabelFrame &f0)
 {
     const int tid = cta.tid(), nthr = cta.nthr();
+    LabelFrame f = f0;
     const uint32_t cap = (uint32_t)f.max_runs;
 
     // P1: runs per row
@@ -233,6 +234,8 @@ YSMR_HD void label_frame(Cta &cta, const LabelFrame &f)
         if (tid == 0) { cta.atomic_or_i32(f.status, LABEL_ST_RUN_OVERFLOW); *f.blob_count = 0; f.counts[0] = n_runs; }
         return;
     }
+    // The union-find arrays move to CTA-local fast memory when the frame's runs fit there (device policy: shared memory).
+    cta.relocate(f, n_runs);
     // P2: write runs
     for (int y = tid; y < f.h; y += nthr)
         write_row_runs(f.img + (int64_t)y * f.ww, f.ww, f.w, y, f.row_start[y], cap, f.rx0, f.rx1, f.ry);
