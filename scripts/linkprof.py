@@ -21,4 +21,11 @@ for rep in range(2):
     names=['dets+sync1','row minima','col winners','outcome+vote','predsum+row','mode+exp','total+div','out+push','estimate','-']
     tot=sum(pc[:12])
     for i in range(9): print('  %-20s %8.0f cyc/frame'%(names[i], pc[i]/max(pc[12],1)))
-    print('  total cyc/frame', tot/max(pc[12],1))
+    print('  total cyc/frame', sum(pc[:9])/max(pc[12],1))
+# association regimes of the scene: n tracks (rows per frame) against m detections
+fr_ids = np.asarray(rows['frame']); npf = np.bincount(fr_ids, minlength=F)
+m = counts.cpu().numpy().astype(int)
+n_before = np.concatenate([[0], npf[:-1]])          # tracks alive when the frame's association runs
+print('frames n==m', int((n_before == m).sum()), 'n>m', int((n_before > m).sum()), 'n<m', int((n_before < m).sum()))
+print('frames where track count changes', int((np.diff(npf) != 0).sum()), 'mean n', npf.mean(), 'mean m', m.mean())
+print('hist of n-m', np.unique(n_before - m, return_counts=True))
