@@ -635,6 +635,9 @@ __global__ void __launch_bounds__(GD_WARPS * 32, GD_MIN_CTAS) gauss_decide_kerne
             case 9: gd_window<9, TAIL>(win, r, m, col_tail); break;
             default: gd_window<10, TAIL>(win, r, m, col_tail); break;
         }
+        // keep r in its own registers across the merge: otherwise slot 10 of the window shares them in one case and every
+        // other case pays eight moves to relocate it (seen in the SASS)
+        asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]));
         const uint32_t bits = gd_decide(m, bf, c_mask, c_mark);
         if (s >= 10) *dst = (uint8_t)bits;
         dst += dec_pitch;
