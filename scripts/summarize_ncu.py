@@ -32,7 +32,9 @@ def launches(src, dst, cmd):
                 name = d['Kernel Name']
                 agg[name].append(v)
                 geo[name] = (d.get('Grid Size', ''), d.get('Block Size', ''))
-    ours = {k: v for k, v in agg.items() if OURS in k or k.startswith('void ysmr')}
+    names = ('blur_prepass', 'plane_margins', 'gauss_decide', 'pack_masks', 'label_kernel', 'geometry', 'link_kernel', 'link_reset',
+             'scalar_decide', 'frame_moments', 'moving_threshold', 'frontend_tile', 'unpack_bits')
+    ours = {k: v for k, v in agg.items() if OURS in k or k.startswith('void ysmr') or any(n in k for n in names)}
     total = sum(sum(v) for v in ours.values())
     with open(dst, 'w') as f:
         f.write(f'# ncu launch list\n\nCommand: `{cmd}`\n\n')
@@ -42,6 +44,12 @@ def launches(src, dst, cmd):
         for k, v in sorted(ours.items(), key=lambda kv: -sum(kv[1])):
             short = k.split('(')[0].replace('void ', '')
             f.write(f'| `{short}` | {len(v)} | {sum(v):.3f} | {sum(v) / len(v):.4f} | {100 * sum(v) / total:.1f} % | {geo[k][0]} | {geo[k][1]} |\n')
+        det = {k: v for k, v in ours.items() if 'link_' not in k}
+        dtot = sum(sum(v) for v in det.values())
+        f.write('\nIn the un-profiled run `link_kernel` sits on its own stream and SM and overlaps detection of the next chunk, so '
+                'the step time is the detection stream. Shares of the detection stream alone: ')
+        f.write(', '.join(f"`{k.split('(')[0].replace('void ', '')}` {100 * sum(v) / dtot:.1f} %"
+                          for k, v in sorted(det.items(), key=lambda kv: -sum(kv[1]))) + '.\n')
         f.write(f'\nRaw list: `{os.path.basename(src)}` (same directory).\n')
     print(open(dst).read())
 
