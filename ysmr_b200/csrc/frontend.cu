@@ -593,15 +593,16 @@ __global__ void __launch_bounds__(GD_WARPS * 32, GD_MIN_CTAS) gauss_decide_kerne
     uint32_t u0 = __ldg(reinterpret_cast<const uint32_t *>(src));
     uint32_t u1 = n_steps > 1 ? __ldg(reinterpret_cast<const uint32_t *>(src + pitch)) : 0u;
     src += 2 * (int64_t)pitch;
+    // halo words travel one group of 8 rows ahead of their use, like the main words travel two rows ahead
+    uint32_t hw = hk < n_steps ? __ldg(reinterpret_cast<const uint32_t *>(hsrc)) : 0u;
+    hsrc += GD_RING * (int64_t)pitch;
     int j = 0;
     for (int s = 0; s < n_steps; ++s) {
         const int slot = s & (GD_RING - 1);
         if (slot == 0) {
             __syncwarp();                         // the row pass of the previous step has read the halo zones
-            if (s + hk < n_steps) {
-                const uint32_t hw = __ldg(reinterpret_cast<const uint32_t *>(hsrc));
-                *reinterpret_cast<float4 *>(hdst) = u8x4_to_float4(hw);
-            }
+            *reinterpret_cast<float4 *>(hdst) = u8x4_to_float4(hw);
+            if (s + GD_RING + hk < n_steps) hw = __ldg(reinterpret_cast<const uint32_t *>(hsrc));
             hsrc += GD_RING * (int64_t)pitch;
         }
         const uint32_t u = u0;
