@@ -38,7 +38,8 @@ def parse():
     ap.add_argument('--frames', type=int, default=9000, help='frames per GPU (configs[1]: 9000)')
     ap.add_argument('--channels', type=int, default=3, choices=[1, 3])
     ap.add_argument('--cells', type=int, default=50)
-    ap.add_argument('--batch', type=int, default=592, help='frames per detect launch')
+    ap.add_argument('--batch', type=int, default=0,
+                    help='frames per detect launch (0: 1184 on one GPU, 592 = one chunk of the streamed hand-over on several)')
     ap.add_argument('--cpu-frames', type=int, default=900, help='frames of the bounded CPU sample (about 15 s)')
     ap.add_argument('--e2e-frames', type=int, default=1000, help='frames in the pinned host buffer of the e2e leg')
     ap.add_argument('--multi', default='stream', choices=['stream', 'gather'],
@@ -194,6 +195,8 @@ def main():
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
+    if not args.batch:
+        args.batch = 1184 if world == 1 else 592
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
@@ -428,11 +431,14 @@ def main():
         host_np = host.numpy()
         rows_out = np.empty(E * 160, ROW_DTYPE)
         calls = (F + E - 1) // E
+        # host streaming uses the chunk size of the drop-in (ysmr_b200/track_eval.py): small chunks keep the H2D copy of chunk
+        # i+1 under the kernels of chunk i and the exposed tail short
+        ctx_e = Context(H, W, Cn, local, max_batch=256, max_blobs=MB, max_tracks=MT)
         def e2e_step():
-            ctx.reset()
+            ctx_e.reset()
             got = 0
             for c in range(calls):
-                got += len(ctx.track_host(host_np, c * E, rows_capacity=len(rows_out), rows_out=rows_out))
+                got += len(ctx_e.track_host(host_np, c * E, rows_capacity=len(rows_out), rows_out=rows_out))
             return got
         e2e_step()
         torch.cuda.synchronize()
