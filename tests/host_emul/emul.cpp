@@ -77,6 +77,7 @@ struct HostCta {
         return s;
     }
     uint32_t atomic_min(uint32_t *p, uint32_t v) const { uint32_t o = *p; if (v < o) *p = v; return o; }
+    void atomic_add(uint32_t *p, uint32_t v) const { *p += v; }
     void atomic_and(uint32_t *p, uint32_t m) const { *p &= m; }
     void atomic_or_i32(int32_t *p, int32_t v) const { *p |= v; }
 };

@@ -30,6 +30,7 @@ struct DevCta {
     __device__ int nthr() const { return blockDim.x; }
     __device__ void sync() const { __syncthreads(); }
     __device__ uint32_t atomic_min(uint32_t *p, uint32_t v) const { return atomicMin(p, v); }
+    __device__ void atomic_add(uint32_t *p, uint32_t v) const { atomicAdd(p, v); }
     __device__ void atomic_and(uint32_t *p, uint32_t m) const { atomicAnd(p, m); }
     __device__ void atomic_or_i32(int32_t *p, int32_t v) const { atomicOr(p, v); }
 

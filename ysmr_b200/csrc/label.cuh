@@ -75,29 +75,6 @@ YSMR_HD int popc32(uint32_t v)
 #endif
 }
 
-// number of runs that START in this row.  Words are fetched four at a time (independent loads in flight; the masks are
-// sparse, so an all-zero group is skipped with one test).
-YSMR_HD uint32_t count_row_runs(const uint32_t *row, int ww)
-{
-    uint32_t n = 0, carry = 0;
-    int i = 0;
-    for (; i + 4 <= ww; i += 4) {
-        const uint32_t b0 = row[i], b1 = row[i + 1], b2 = row[i + 2], b3 = row[i + 3];
-        if ((b0 | b1 | b2 | b3) == 0u) { carry = 0; continue; }
-        n += popc32(b0 & ~((b0 << 1) | carry));
-        n += popc32(b1 & ~((b1 << 1) | (b0 >> 31)));
-        n += popc32(b2 & ~((b2 << 1) | (b1 >> 31)));
-        n += popc32(b3 & ~((b3 << 1) | (b2 >> 31)));
-        carry = b3 >> 31;
-    }
-    for (; i < ww; ++i) {
-        const uint32_t b = row[i];
-        n += popc32(b & ~((b << 1) | carry));
-        carry = b >> 31;
-    }
-    return n;
-}
-
 // runs of one word appended at index k (continuing a run that is open from the previous word)
 YSMR_HD void write_word_runs(uint32_t b, int base, int y, uint32_t &k, bool &open, uint32_t cap, uint16_t *x0s, uint16_t *x1s,
                              uint16_t *ys)
@@ -224,9 +201,29 @@ YSMR_HD void label_frame(Cta &cta, const LabelFrame &f0)
     LabelFrame f = f0;
     const uint32_t cap = (uint32_t)f.max_runs;
 
-    // P1: runs per row
-    for (int y = tid; y < f.h; y += nthr) f.row_start[y] = count_row_runs(f.img + (int64_t)y * f.ww, f.ww);
-    if (tid == 0) f.row_start[f.h] = 0;
+    // P1: runs per row.  The CTA streams the bit image once, word by word (consecutive threads read consecutive words); the
+    // masks are sparse, so only the few non-zero words look at their left neighbour and add to their row's counter.
+    for (int y = tid; y <= f.h; y += nthr) f.row_start[y] = 0;
+    cta.sync();
+    {
+        const int n_words = f.h * f.ww;
+        for (int base = tid; base < n_words; base += 4 * nthr) {     // four independent loads in flight per thread
+            uint32_t b[4];
+#ifdef __CUDA_ARCH__
+#pragma unroll
+#endif
+            for (int k = 0; k < 4; ++k) { const int i = base + k * nthr; b[k] = i < n_words ? f.img[i] : 0u; }
+            if ((b[0] | b[1] | b[2] | b[3]) == 0u) continue;
+            for (int k = 0; k < 4; ++k) {
+                if (b[k] == 0u) continue;
+                const int i = base + k * nthr;
+                const int y = i / f.ww, xw = i - y * f.ww;
+                const uint32_t carry = xw ? f.img[i - 1] >> 31 : 0u;
+                const uint32_t n = (uint32_t)popc32(b[k] & ~((b[k] << 1) | carry));
+                if (n) cta.atomic_add(&f.row_start[y], n);
+            }
+        }
+    }
     cta.sync();
     uint32_t n_runs = cta.exclusive_scan(f.row_start, f.h + 1);
     bool overflow = n_runs > cap;
@@ -238,7 +235,8 @@ YSMR_HD void label_frame(Cta &cta, const LabelFrame &f0)
     cta.relocate(f, n_runs);
     // P2: write runs
     for (int y = tid; y < f.h; y += nthr)
-        write_row_runs(f.img + (int64_t)y * f.ww, f.ww, f.w, y, f.row_start[y], cap, f.rx0, f.rx1, f.ry);
+        if (f.row_start[y + 1] != f.row_start[y])                   // most rows are empty
+            write_row_runs(f.img + (int64_t)y * f.ww, f.ww, f.w, y, f.row_start[y], cap, f.rx0, f.rx1, f.ry);
     cta.sync();
 
     uint32_t nk = n_runs;
