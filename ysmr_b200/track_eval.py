@@ -2,9 +2,10 @@
 
 Same signature, same return tuple ``(df_sorted, fps_of_file, frame_height, frame_width, list_csv_path)`` or ``None`` on
 any failure, same ``<result_folder>/<stem>_list.csv``.  What changes is the body of the ``while True`` loop
-(track_eval.py:156-366): frames are decoded by cv2.VideoCapture exactly as before, but collected in a pinned host
-buffer and handed, a chunk at a time, to ``ysmr_track_host`` (include/ysmr_b200.h), which runs detection and linking on
-the GPU and returns the rows the loop would have appended to ``coords``.
+(track_eval.py:156-366): frames are decoded by cv2.VideoCapture exactly as before, but by a reader thread into one of two
+pinned host buffers, and handed, a chunk at a time, to ``ysmr_track_host`` (include/ysmr_b200.h), which runs detection
+and linking on the GPU (H2D copies double-buffered under the kernels) and returns the rows the loop would have appended
+to ``coords``; decoding of the next chunk overlaps the GPU work of the current one.
 
 Unsupported on this path (the function logs and returns None rather than silently diverging):
 'include luminosity in tracking calculation' (broken with GSFF in the reference itself), colour
@@ -108,7 +109,35 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
         cap.release()
         return None
 
-    keep, buf = _pinned_frames(chunk_frames, frame_height, frame_width)
+    # Ingest: a reader thread decodes chunk i+1 into the other pinned buffer while the GPU works on chunk i
+    # (cv2.VideoCapture.read and the ctypes call both release the GIL); the queues hand the two buffers back and forth.
+    import queue
+    import threading
+    keep = [_pinned_frames(chunk_frames, frame_height, frame_width) for _ in range(2)]
+    free_q, full_q = queue.Queue(), queue.Queue()
+    for i in range(2):
+        free_q.put(i)
+    stop_reading = threading.Event()
+
+    def reader():
+        try:
+            while not stop_reading.is_set():
+                i = free_q.get()
+                if i is None:
+                    return
+                b = keep[i][1]
+                n = 0
+                while n < chunk_frames and not stop_reading.is_set():
+                    ret, frame = cap.read()
+                    if not ret:
+                        full_q.put((i, n, True))
+                        return
+                    b[n] = frame
+                    n += 1
+                full_q.put((i, n, False))
+        except Exception as ex:                      # surfaces in the consumer
+            full_q.put(ex)
+
     rows_out = np.empty(min(chunk_frames * max_tracks, 1 << 22), ROW_DTYPE)
     pending = []            # rows not yet written (flushed every 'list save length interval' rows like the reference)
     n_pending = 0
@@ -116,24 +145,25 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
     error_during_read = False
     last_live = 0
     done = False
+    th = threading.Thread(target=reader, name='ysmr-b200-decode', daemon=True)
+    th.start()
     try:
         while not done:
-            n = 0
-            while n < chunk_frames:
-                ret, frame = cap.read()
-                if not ret:
-                    done = True
-                    total = curr_frame_count + n
-                    if (frame_count == total + 1 or frame_count == total) and frame_count >= settings['minimal frame count']:
-                        logger.debug('Frames from file {} read.'.format(os.path.basename(video_path)))
-                    else:
-                        logger.critical('Error during cap.read() with file {}'.format(video_path))
-                        error_during_read = settings['stop evaluation on error']
-                    break
-                buf[n] = frame
-                n += 1
+            item = full_q.get()
+            if isinstance(item, Exception):
+                raise item
+            i, n, done = item
+            buf = keep[i][1]
+            if done:
+                total = curr_frame_count + n
+                if (frame_count == total + 1 or frame_count == total) and frame_count >= settings['minimal frame count']:
+                    logger.debug('Frames from file {} read.'.format(os.path.basename(video_path)))
+                else:
+                    logger.critical('Error during cap.read() with file {}'.format(video_path))
+                    error_during_read = settings['stop evaluation on error']
             if n:
                 rows = ctx.track_host(buf[:n], curr_frame_count, rows_capacity=len(rows_out), rows_out=rows_out)
+                free_q.put(i)
                 pending.append(rows.copy()); n_pending += len(rows)
                 curr_frame_count += n
                 last_live = ctx.live_tracks()[0]
@@ -144,9 +174,11 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
             listio.append_rows(list_name, np.concatenate(pending))
     except Exception as ex:
         logger.exception('GPU tracking failed for {}: {}'.format(video_path, ex))
+        stop_reading.set(); free_q.put(None); th.join(timeout=30)
         cap.release()
         ctx.close()
         return None
+    stop_reading.set(); free_q.put(None); th.join(timeout=30)
     cap.release()
     ctx.close()
     del keep
