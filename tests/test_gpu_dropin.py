@@ -22,8 +22,8 @@ def _write_ffv1(path, grey, fps):
     vw.release()
 
 
-@pytest.mark.parametrize('name', ['small_wod', 'small_dol'])
-def test_track_bacteria_dropin(tmp_path, name):
+@pytest.mark.parametrize('name,sink', [('small_wod', 'append'), ('small_dol', 'append'), ('small_wod', 'once')])
+def test_track_bacteria_dropin(tmp_path, name, sink):
     from ysmr_b200.track_eval import track_bacteria
     g = np.load(os.path.join(GOLDEN, f'e2e_{name}.npz'))
     kw = {k[6:]: g[k].item() for k in g.files if k.startswith('scene_')}
@@ -33,7 +33,7 @@ def test_track_bacteria_dropin(tmp_path, name):
     _write_ffv1(video, grey, cfg.fps)
     settings = {'white bacteria on dark background': bool(g['white_on_dark']), 'threshold offset for detection': int(g['offset']),
                 'adaptive double threshold': float(g['adt']), 'minimal frame count': 10, 'display video analysis': False}
-    res = track_bacteria(video, settings, str(tmp_path), chunk_frames=64, max_blobs=512, max_tracks=512)
+    res = track_bacteria(video, settings, str(tmp_path), chunk_frames=64, max_blobs=512, max_tracks=512, row_sink=sink)
     assert res is not None
     df, fps, fh, fw, csv = res
     assert (fps, fh, fw) == (float(g['fps']), int(g['frame_height']), int(g['frame_width']))

@@ -54,6 +54,12 @@ def append_rows(csv_path, rows):
     float32 results of cv2.minAreaRect widened to Python floats, or the ints 0,0,0 of an unmatched track."""
     if len(rows) == 0:
         return
+    with open(csv_path, 'a', newline='') as fh:
+        fh.write(format_rows(rows))
+
+
+def format_rows(rows):
+    """The text append_rows writes for these rows."""
     ids = rows['track_id'].tolist(); frames = rows['frame'].tolist()
     xs = rows['x'].tolist(); ys = rows['y'].tolist()
     ws = rows['w'].astype(np.float64).tolist(); hs = rows['h'].astype(np.float64).tolist()
@@ -64,8 +70,7 @@ def append_rows(csv_path, rows):
             out.append('{},{},{!r},{!r},0,0,0\n'.format(i, t, x, y))
         else:
             out.append('{},{},{!r},{!r},{!r},{!r},{!r}\n'.format(i, t, x, y, w, h, d))
-    with open(csv_path, 'a', newline='') as fh:
-        fh.write(''.join(out))
+    return ''.join(out)
 
 
 def sort_list(csv_path, save_file=True):
@@ -73,6 +78,23 @@ def sort_list(csv_path, save_file=True):
     import pandas as pd
     with open(csv_path, 'r', newline='\n') as fh:
         df = pd.read_csv(fh, sep=',', header=0, usecols=list(DTYPES.keys()), dtype=DTYPES)
+    df.sort_values(by=['TRACK_ID', 'POSITION_T'], inplace=True, na_position='first')
+    df.reset_index(drop=True, inplace=True)
+    if save_file:
+        with open(csv_path, 'w+', newline='\n') as fh:
+            df.to_csv(fh, index=False, encoding='utf-8')
+    return df
+
+
+def write_sorted(csv_path, rows, save_file=True):
+    """Row sink with a single write: the rows of the whole video (api.ROW_DTYPE, emission order) are
+    formatted as the hot loop would have appended them, parsed back IN MEMORY by the same pandas call as
+    helper_file.get_data, sorted by (TRACK_ID, POSITION_T) and written once.  The parse cannot be skipped: pandas' default
+    float parser is not round-trip exact (10.494321823120117 comes back as 10.494321823120115), and that last-digit
+    perturbation is part of the reference's file.  tests/test_listio.py compares the bytes with append_rows + sort_list."""
+    import io
+    import pandas as pd
+    df = pd.read_csv(io.StringIO(HEADER + format_rows(rows)), sep=',', header=0, usecols=list(DTYPES.keys()), dtype=DTYPES)
     df.sort_values(by=['TRACK_ID', 'POSITION_T'], inplace=True, na_position='first')
     df.reset_index(drop=True, inplace=True)
     if save_file:

@@ -47,7 +47,7 @@ def _pinned_frames(n, h, w):
 
 
 def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, chunk_frames=256, max_blobs=4096,
-                   max_tracks=8192):
+                   max_tracks=8192, row_sink='append'):
     import cv2
     from .api import ROW_DTYPE, Context
     logger = logging.getLogger('ysmr').getChild(__name__)
@@ -57,6 +57,9 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
         return None
     if not os.path.isfile(video_path):
         logger.critical('File {} does not exist'.format(video_path))
+        return None
+    if row_sink not in ('append', 'once'):
+        logger.critical("row_sink must be 'append' or 'once', not {!r}".format(row_sink))
         return None
     try:
         cap = cv2.VideoCapture(video_path)
@@ -167,10 +170,13 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
                 pending.append(rows.copy()); n_pending += len(rows)
                 curr_frame_count += n
                 last_live = ctx.live_tracks()[0]
-                if n_pending >= settings['list save length interval']:
+                # row_sink 'append' (default): the reference's life cycle, text appended every 'list save length interval'
+                # rows and sorted through a read-back at the end; 'once': rows stay in memory and the sorted file is
+                # written a single time (listio.write_sorted) -- same bytes, no intermediate file traffic
+                if row_sink == 'append' and n_pending >= settings['list save length interval']:
                     listio.append_rows(list_name, np.concatenate(pending))
                     pending, n_pending = [], 0
-        if pending:
+        if pending and row_sink == 'append':
             listio.append_rows(list_name, np.concatenate(pending))
     except Exception as ex:
         logger.exception('GPU tracking failed for {}: {}'.format(video_path, ex))
@@ -193,7 +199,11 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
     if last_live == 0:            # track_eval.py:388-392: no object alive after the last frame
         logger.warning('Did not track any objects. File: {}'.format(video_path))
         return None
-    df_for_eval = listio.sort_list(list_name, save_file=not settings['delete .csv file after analysis'])
+    if row_sink == 'append':
+        df_for_eval = listio.sort_list(list_name, save_file=not settings['delete .csv file after analysis'])
+    else:
+        all_rows = np.concatenate(pending) if pending else np.empty(0, ROW_DTYPE)
+        df_for_eval = listio.write_sorted(list_name, all_rows, save_file=not settings['delete .csv file after analysis'])
     logger.info('frames: {:>6} of {:>6}, csv: {}'.format(curr_frame_count, frame_count, list_name))
     if error_during_read:
         logger.critical('Error during read, stopping before evaluation. File: {}'.format(video_path))
