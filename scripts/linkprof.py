@@ -2,7 +2,9 @@ import numpy as np, torch, sys
 sys.path.insert(0,'.')
 from ysmr_b200.api import Context
 from ysmr_b200.synth import SceneConfig, make_scene, render_frames_torch
-F=1024
+import os
+F=int(os.environ.get('LINKPROF_FRAMES','1024'))
+PLAIN=bool(os.environ.get('LINKPROF_PLAIN'))
 scene=make_scene(SceneConfig(n_frames=F,n_cells=50,seed=0))
 fr=torch.empty((F,922,1228),dtype=torch.uint8,device='cuda')
 for a in range(0,F,128): render_frames_torch(scene,a,a+128,'cuda',1,out=fr[a:a+128])
@@ -12,7 +14,7 @@ for a in range(0,F,256):
     c,b=ctx.detect(fr[a:a+256],a); cs.append(c); bs.append(b)
 counts=torch.cat(cs); blobs=torch.cat(bs)
 for rep in range(2):
-    ctx.reset(); ctx.set_profiling(True, link_phases=True)
+    ctx.reset(); ctx.set_profiling(True, link_phases=not PLAIN)
     torch.cuda.synchronize()
     e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
     e0.record(); rows=ctx.link(counts,blobs,0,F*100); e1.record(); torch.cuda.synchronize()
