@@ -495,13 +495,6 @@ constexpr int GD_RING = 8;
 constexpr int GD_ROWF = 144;                      // floats per ring slot: 8 halo | 128 | 8 halo
 constexpr float GD_MAGIC = 12582912.0f;           // 1.5 * 2^23
 
-__device__ __forceinline__ float sub_sat(float a, float b)
-{
-    float d;
-    asm("sub.sat.f32 %0, %1, %2;" : "=f"(d) : "f"(a), "f"(b));
-    return d;
-}
-
 __device__ __forceinline__ float4 u8x4_to_float4(uint32_t u)
 {
     // 0x4B000000 | byte is the float 2^23 + byte
