@@ -589,53 +589,64 @@ __global__ void __launch_bounds__(GD_WARPS * 32, GD_MIN_CTAS) gauss_decide_kerne
     // halo words travel one group of 8 rows ahead of their use, like the main words travel two rows ahead
     uint32_t hw = hk < n_steps ? __ldg(reinterpret_cast<const uint32_t *>(hsrc)) : 0u;
     hsrc += GD_RING * (int64_t)pitch;
+    // Two steps per iteration: the step counter, the window-slot dispatch and the pointer updates are paid once per two
+    // rows.  (n_steps may be odd: the second half of the last iteration then works on a stale row and stores nothing.)
     int j = 0;
-    for (int s = 0; s < n_steps; ++s) {
-        const int slot = s & (GD_RING - 1);
+    for (int s = 0; s < n_steps; s += 2) {
+        const int slot = s & (GD_RING - 1);       // even, so slot + 1 is inside the ring
         if (slot == 0) {
             __syncwarp();                         // the row pass of the previous step has read the halo zones
             *reinterpret_cast<float4 *>(hdst) = u8x4_to_float4(hw);
             if (s + GD_RING + hk < n_steps) hw = __ldg(reinterpret_cast<const uint32_t *>(hsrc));
             hsrc += GD_RING * (int64_t)pitch;
         }
-        const uint32_t u = u0;
-        u0 = u1;
-        if (s + 2 < n_steps) u1 = __ldg(reinterpret_cast<const uint32_t *>(src));
-        src += pitch;
-        float *row = ring + slot * GD_ROWF;
-        *reinterpret_cast<float4 *>(row + 8 + 4 * lane) = u8x4_to_float4(u);
+        const uint32_t ua = u0, ub = u1;
+        if (s + 2 < n_steps) u0 = __ldg(reinterpret_cast<const uint32_t *>(src));
+        if (s + 3 < n_steps) u1 = __ldg(reinterpret_cast<const uint32_t *>(src + pitch));
+        src += 2 * (int64_t)pitch;
+        float *row0 = ring + slot * GD_ROWF, *row1 = row0 + GD_ROWF;
+        *reinterpret_cast<float4 *>(row0 + 8 + 4 * lane) = u8x4_to_float4(ua);
+        *reinterpret_cast<float4 *>(row1 + 8 + 4 * lane) = u8x4_to_float4(ub);
         __syncwarp();
-        float a[20];
+        float r0[4], r1[4], m0[4], m1[4];
+        {
+            float a[20];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) {
-            const float4 t4 = *reinterpret_cast<const float4 *>(row + 4 * lane + 4 * q);
-            a[4 * q] = t4.x; a[4 * q + 1] = t4.y; a[4 * q + 2] = t4.z; a[4 * q + 3] = t4.w;
+            for (int q = 0; q < 5; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(row0 + 4 * lane + 4 * q);
+                a[4 * q] = t4.x; a[4 * q + 1] = t4.y; a[4 * q + 2] = t4.z; a[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r0[k] = gauss_row<TAIL>(&a[3 + k], row_tail);
         }
-        // blurred values of the output row (written 5 steps ago by this very lane)
-        const float4 bf = *reinterpret_cast<const float4 *>(ring + ((s + 3) & (GD_RING - 1)) * GD_ROWF + 8 + 4 * lane);
-        float r[4], m[4];
+        {
+            float a[20];
 #pragma unroll
-        for (int k = 0; k < 4; ++k) r[k] = gauss_row<TAIL>(&a[3 + k], row_tail);
+            for (int q = 0; q < 5; ++q) {
+                const float4 t4 = *reinterpret_cast<const float4 *>(row1 + 4 * lane + 4 * q);
+                a[4 * q] = t4.x; a[4 * q + 1] = t4.y; a[4 * q + 2] = t4.z; a[4 * q + 3] = t4.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) r1[k] = gauss_row<TAIL>(&a[3 + k], row_tail);
+        }
+        // blurred values of the two output rows (written 5 steps before by this very lane)
+        const float4 bf0 = *reinterpret_cast<const float4 *>(ring + ((s + 3) & (GD_RING - 1)) * GD_ROWF + 8 + 4 * lane);
+        const float4 bf1 = *reinterpret_cast<const float4 *>(ring + ((s + 4) & (GD_RING - 1)) * GD_ROWF + 8 + 4 * lane);
+#define GD_CASE(J) case J: gd_window<J, TAIL>(win, r0, m0, col_tail); gd_window<(J + 1) % 11, TAIL>(win, r1, m1, col_tail); break;
         switch (j) {
-            case 0: gd_window<0, TAIL>(win, r, m, col_tail); break;
-            case 1: gd_window<1, TAIL>(win, r, m, col_tail); break;
-            case 2: gd_window<2, TAIL>(win, r, m, col_tail); break;
-            case 3: gd_window<3, TAIL>(win, r, m, col_tail); break;
-            case 4: gd_window<4, TAIL>(win, r, m, col_tail); break;
-            case 5: gd_window<5, TAIL>(win, r, m, col_tail); break;
-            case 6: gd_window<6, TAIL>(win, r, m, col_tail); break;
-            case 7: gd_window<7, TAIL>(win, r, m, col_tail); break;
-            case 8: gd_window<8, TAIL>(win, r, m, col_tail); break;
-            case 9: gd_window<9, TAIL>(win, r, m, col_tail); break;
-            default: gd_window<10, TAIL>(win, r, m, col_tail); break;
+            GD_CASE(0) GD_CASE(1) GD_CASE(2) GD_CASE(3) GD_CASE(4) GD_CASE(5) GD_CASE(6) GD_CASE(7) GD_CASE(8) GD_CASE(9)
+            default: gd_window<10, TAIL>(win, r0, m0, col_tail); gd_window<0, TAIL>(win, r1, m1, col_tail); break;
         }
-        // keep r in its own registers across the merge: otherwise slot 10 of the window shares them in one case and every
-        // other case pays eight moves to relocate it (seen in the SASS)
-        asm volatile("" : "+f"(r[0]), "+f"(r[1]), "+f"(r[2]), "+f"(r[3]));
-        const uint32_t bits = gd_decide(m, bf, c_mask, c_mark);
-        if (s >= 10) *dst = (uint8_t)bits;
-        dst += dec_pitch;
-        j = j == 10 ? 0 : j + 1;
+#undef GD_CASE
+        // keep the row results in their own registers across the merge: otherwise one window slot shares them in one case and
+        // every other case pays moves to relocate it (seen in the SASS)
+        asm volatile("" : "+f"(r0[0]), "+f"(r0[1]), "+f"(r0[2]), "+f"(r0[3]), "+f"(r1[0]), "+f"(r1[1]), "+f"(r1[2]), "+f"(r1[3]));
+        const uint32_t bits0 = gd_decide(m0, bf0, c_mask, c_mark);
+        const uint32_t bits1 = gd_decide(m1, bf1, c_mask, c_mark);
+        if (s >= 10) *dst = (uint8_t)bits0;
+        if (s + 1 >= 10 && s + 1 < n_steps) dst[dec_pitch] = (uint8_t)bits1;
+        dst += 2 * dec_pitch;
+        j += 2; j = j >= 11 ? j - 11 : j;
     }
 }
 
