@@ -583,9 +583,12 @@ __global__ void __launch_bounds__(GD_WARPS * 32, GD_MIN_CTAS) gauss_decide_kerne
 #pragma unroll
     for (int i = 0; i < 11; ++i) win[i][0] = win[i][1] = make_float2(0.f, 0.f);
 
+    // main words travel four rows (two iterations) ahead of their use
     uint32_t u0 = __ldg(reinterpret_cast<const uint32_t *>(src));
     uint32_t u1 = n_steps > 1 ? __ldg(reinterpret_cast<const uint32_t *>(src + pitch)) : 0u;
-    src += 2 * (int64_t)pitch;
+    uint32_t u2 = n_steps > 2 ? __ldg(reinterpret_cast<const uint32_t *>(src + 2 * (int64_t)pitch)) : 0u;
+    uint32_t u3 = n_steps > 3 ? __ldg(reinterpret_cast<const uint32_t *>(src + 3 * (int64_t)pitch)) : 0u;
+    src += 4 * (int64_t)pitch;
     // halo words travel one group of 8 rows ahead of their use, like the main words travel two rows ahead
     uint32_t hw = hk < n_steps ? __ldg(reinterpret_cast<const uint32_t *>(hsrc)) : 0u;
     hsrc += GD_RING * (int64_t)pitch;
@@ -601,8 +604,9 @@ __global__ void __launch_bounds__(GD_WARPS * 32, GD_MIN_CTAS) gauss_decide_kerne
             hsrc += GD_RING * (int64_t)pitch;
         }
         const uint32_t ua = u0, ub = u1;
-        if (s + 2 < n_steps) u0 = __ldg(reinterpret_cast<const uint32_t *>(src));
-        if (s + 3 < n_steps) u1 = __ldg(reinterpret_cast<const uint32_t *>(src + pitch));
+        u0 = u2; u1 = u3;
+        if (s + 4 < n_steps) u2 = __ldg(reinterpret_cast<const uint32_t *>(src));
+        if (s + 5 < n_steps) u3 = __ldg(reinterpret_cast<const uint32_t *>(src + pitch));
         src += 2 * (int64_t)pitch;
         float *row0 = ring + slot * GD_ROWF, *row1 = row0 + GD_ROWF;
         *reinterpret_cast<float4 *>(row0 + 8 + 4 * lane) = u8x4_to_float4(ua);
