@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define YSMR_ABI_VERSION 2
+#define YSMR_ABI_VERSION 3
 
 enum {
     YSMR_OK = 0,
@@ -155,6 +155,12 @@ int ysmr_track_host(ysmr_ctx *ctx, const uint8_t *h_frames, int n_frames, int64_
  * (internally forks a second stream so the linker of chunk i overlaps detection of chunk i+1). */
 int ysmr_track_device(ysmr_ctx *ctx, const uint8_t *d_frames, int n_frames, int64_t frame_stride, int first_frame,
                       ysmr_row *d_rows, int64_t rows_capacity, int64_t *d_n_rows, void *stream);
+
+/* Development / measurement switches (not needed in production).  YSMR_OPT_FRONTEND_GEN: 4 (default) = the fused
+ * bound-and-refine front-end kernel where it applies, 3 = always the three-kernel front-end of ABI 2 (bench.py's A/B
+ * figure, and tests that hold one against the other). */
+enum { YSMR_OPT_FRONTEND_GEN = 1 };
+int ysmr_set_option(ysmr_ctx *ctx, int option, int value);
 
 /* Number of kernels launched by this context since creation (bench.py's gpu_launches claim). */
 int64_t ysmr_launch_count(const ysmr_ctx *ctx);

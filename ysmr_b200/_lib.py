@@ -68,6 +68,7 @@ EXPORTS = {
                                   C.POINTER(C.c_int64)]),
     'ysmr_track_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                                     C.c_void_p, C.c_void_p]),
+    'ysmr_set_option': (C.c_int, [C.c_void_p, C.c_int, C.c_int]),
     'ysmr_launch_count': (C.c_int64, [C.c_void_p]),
     'ysmr_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
     'ysmr_get_profile': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),

@@ -206,6 +206,12 @@ class Context:
                                              int(first_frame), rows_out.ctypes.data_as(C.c_void_p), cap, C.byref(k)))
         return rows_out[:k.value]
 
+    OPT_FRONTEND_GEN = 1
+
+    def set_option(self, option, value):
+        """Development / measurement switches of the library (include/ysmr_b200.h: YSMR_OPT_*)."""
+        self._check(self.lib.ysmr_set_option(self._h, int(option), int(value)))
+
     def launch_count(self):
         return int(self.lib.ysmr_launch_count(self._h))
 

@@ -50,7 +50,7 @@ struct ysmr_ctx {
     int window = 0;               // mean/std moving window (frames)
     int gains_affine = 1;         // all uploaded FIR gains are affine in the tap index (required by the fast linker)
     int link_fast = 1;            // YSMR_LINK=general disables the shared-memory fast path of the linker (tests)
-    int use_tile = 0;             // YSMR_FRONTEND=tile: run the simple tile kernel instead of the production kernels
+    int frontend_gen = 4;         // 3: force the three-kernel front-end (ysmr_set_option, A/B measurements in bench.py)
     cudaStream_t s_tail = nullptr; cudaEvent_t ev_tail_fork = nullptr, ev_tail_join = nullptr;   // K1b tail-strip launch
     uint8_t *plane = nullptr; int64_t plane_stride = 0; int pitch = 0;          // blurred planes (K1a -> K1b)
     uint8_t *decisions = nullptr; int64_t dec_stride = 0; int dec_pitch = 0;    // decision bytes (K1b -> K1c)
@@ -193,7 +193,6 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     ysmr_ctx *c = new ysmr_ctx();
     c->device = device; c->h = height; c->w = width; c->ww = (width + 31) / 32; c->channels = channels; c->p = *params;
     derive_thresholds(c);
-    { const char *fe = getenv("YSMR_FRONTEND"); c->use_tile = fe && strcmp(fe, "tile") == 0; }
     { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strcmp(lk, "general") == 0); }
 #define CC(expr)                                                                                                       \
     do {                                                                                                               \
@@ -205,6 +204,8 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
         }                                                                                                              \
     } while (0)
     CC(cudaSetDevice(device));
+    CC(fused_frontend_init());                     // per-device kernel attributes (shared-memory opt-in)
+    CC(link_kernel_init());
     const size_t B = (size_t)params->max_batch, H = (size_t)height, WW = (size_t)c->ww, MB = (size_t)params->max_blobs;
     CC(dev_alloc(c, &c->mask_bits, B * H * WW));
     CC(dev_alloc(c, &c->marker_bits, B * H * WW));
@@ -393,13 +394,22 @@ int ysmr_detect(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_t fram
         if (dbg && dbg->d_scalar_thr)
             CU(c, cudaMemcpyAsync(dbg->d_scalar_thr, c->scalar_thr, sizeof(int32_t) * n_frames, cudaMemcpyDeviceToDevice, st));
     }
-    if (c->use_tile || (dbg && (dbg->d_grey || dbg->d_blurred || dbg->d_mean))) {
-        // tile kernel: the only one that can dump grey / blurred / mean.  Unless forced (YSMR_FRONTEND=tile) its masks are
-        // then overwritten by the production kernel below, so the mask dumps always come from the production path.
-        ProfScope ps(c, c->use_tile ? YSMR_PROF_FRONTEND : YSMR_PROF_GEOMETRY, st);
-        CU(c, launch_frontend_tile(fp, st)); c->launches++;
+    const bool fused = c->frontend_gen != 3 && fused_frontend_supported(fp);
+    if (dbg && (dbg->d_mean || (!fused && (dbg->d_grey || dbg->d_blurred)))) {
+        // debug tile kernel: the only one that can dump the rounded Gaussian mean (and grey / blurred when the production
+        // front-end is the three-kernel one).  Its masks are overwritten by the production kernel(s) below, so the mask
+        // dumps always come from the production path.
+        FrontParams ft = fp;
+        if (fused) { ft.dbg_grey = nullptr; ft.dbg_blurred = nullptr; }
+        CU(c, launch_frontend_tile(ft, st)); c->launches++;
     }
-    if (!c->use_tile) {
+    if (fused) {
+        // generation 4: one fused kernel (fused.cu); grey / blurred dumps come from its own shared-memory tiles
+        ProfScope ps(c, YSMR_PROF_FRONTEND, st);
+        CU(c, launch_fused_frontend(fp, st)); c->launches += 1;
+    } else {
+        // generation 3 (three kernels through a padded blurred plane): mean/std mode, widths that are not a multiple of 4,
+        // unaligned frames
         ProfScope ps(c, YSMR_PROF_FRONTEND, st);
         { ProfScope p1(c, YSMR_PROF_K1A, st); CU(c, launch_blur_prepass(fp, st)); c->launches += 2; }
         {
@@ -658,6 +668,13 @@ int ysmr_track_host(ysmr_ctx *c, const uint8_t *h_frames, int n_frames, int64_t 
     *n_rows = n;
     int32_t bits = 0, bad = -1;
     return ysmr_status(c, user, &bits, &bad);
+}
+
+int ysmr_set_option(ysmr_ctx *c, int option, int value)
+{
+    if (!c) return YSMR_E_INVALID;
+    if (option == YSMR_OPT_FRONTEND_GEN && (value == 3 || value == 4)) { c->frontend_gen = value; return YSMR_OK; }
+    return fail(c, YSMR_E_INVALID, "unknown option or value");
 }
 
 int64_t ysmr_launch_count(const ysmr_ctx *c) { return c ? c->launches : 0; }

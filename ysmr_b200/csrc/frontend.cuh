@@ -28,6 +28,11 @@ struct FrontParams {
     uint8_t *dbg_grey, *dbg_blurred, *dbg_mean;
 };
 
+// fused.cu: the generation-4 front-end (one kernel, bound-and-refine)
+bool fused_frontend_supported(const FrontParams &p);
+cudaError_t fused_frontend_init();                                           // per device, from ysmr_create
+cudaError_t launch_fused_frontend(const FrontParams &p, cudaStream_t st);    // 1 launch
+
 cudaError_t launch_frontend_tile(const FrontParams &p, cudaStream_t st);
 cudaError_t launch_blur_prepass(const FrontParams &p, cudaStream_t st);      // K1a + margins: 2 launches
 cudaError_t launch_gauss_decide(const FrontParams &p, cudaStream_t st, cudaStream_t st_tail, int *n_launched);   // K1b

@@ -435,6 +435,7 @@ YSMR_HD void row_minima_serial(const Cta &cta, const LinkState &s, const int32_t
 cudaError_t launch_link(const LinkConfig &c, const LinkState &s, const LinkScratch &x, const LinkIo &io, int first_frame,
                         int n_frames, int allow_fast, cudaStream_t st);
 cudaError_t launch_link_reset(const LinkState &s, int max_tracks, cudaStream_t st);
+cudaError_t link_kernel_init();            // per device: shared-memory opt-in of link_kernel (from ysmr_create)
 #endif
 
 }  // namespace ysmr
