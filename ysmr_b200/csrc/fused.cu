@@ -35,17 +35,21 @@
 #include "frontend.cuh"
 #include "front_arith.cuh"
 
+#include <stdlib.h>
+
 namespace ysmr {
 
 constexpr int FT_THREADS = 256;
 
 struct FusedGeom {
-    int tw, th;                 // tile size: tw % 32 == 0, th % 4 == 0, tw * th <= 65536
+    int tw, th, ltw;            // tile size: tw = 1 << ltw (128 or 256), th % 4 == 0, tw * th <= 65536
     int tiles_x, tiles_y;
     int gp;                     // byte pitch of the grey / blurred tiles: >= tw + 24, gp % 8 == 0, (gp / 8) odd
     int rp;                     // byte pitch of the transposed row-pass bytes: >= th + 8, rp % 4 == 0, (rp / 4) odd
     int t_q;                    // polarised decision threshold (see fused_geometry)
     int off_blur, off_mask, off_list, off_misc;   // shared-memory offsets (bytes); grey tile and row-pass bytes at 0
+    int list_cap;               // candidate list entries
+    int prefetch_dist;          // L2 prefetch distance in CTAs (0: off)
     int smem_bytes;
 };
 
@@ -125,13 +129,48 @@ __device__ __forceinline__ HRow4 hadd(const HRow4 &a, const HRow4 &b)
     return s;
 }
 
-template <int C>
-__device__ __forceinline__ uint32_t grey_word_slow(const uint8_t *frame, int w, int gy, int vx)
+// What the exact decision of one pixel needs (phase 3 and the overflow path of phase 2b).
+struct RefineCtx {
+    uint32_t s_blur;
+    int gp, tw, ltw, mw, n_mask, tx0;
+    int row_tail_from, col_tail_from, t_mask, t_marker;
+    bool inv, two;
+    uint32_t *smask;
+};
+
+// Exact decisions of tile pixel (xx, yy): OpenCV's float32 11x11 Gaussian (front_arith.cuh) around the pixel from the
+// blurred tile, rint, both threshold compares; sets the pixel's bits in the shared mask tiles.
+__device__ __noinline__ void refine_px(const RefineCtx &rc, int idx)
 {
-    uint32_t v = 0;
+    const int yy = idx >> rc.ltw, xx = idx & (rc.tw - 1);
+    const int x = rc.tx0 + xx;
+    const bool row_tail = x >= rc.row_tail_from, col_tail = x >= rc.col_tail_from;
+    const uint32_t a0 = rc.s_blur + yy * rc.gp + 12 + xx - 5;     // tile row yy + 5 - 5, byte column of x - 5
+    const uint32_t al = a0 & ~3u;
+    const uint32_t sel = 0x3210u + 0x1111u * (a0 & 3u);
+    float r[11];
+    int bc = 0;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) v |= grey_px<C>(frame, w, gy, reflect101(vx + k, w)) << (8 * k);
-    return v;
+    for (int j = 0; j < 11; ++j) {
+        const uint32_t ra = al + j * rc.gp;
+        const uint32_t u0 = lds32(ra), u1 = lds32(ra + 4), u2 = lds32(ra + 8), u3 = lds32(ra + 12);
+        const uint32_t v0 = __byte_perm(u0, u1, sel), v1 = __byte_perm(u1, u2, sel), v2 = __byte_perm(u2, u3, sel);
+        float a[11];
+        a[0] = (float)(v0 & 0xFFu); a[1] = (float)((v0 >> 8) & 0xFFu); a[2] = (float)((v0 >> 16) & 0xFFu); a[3] = (float)(v0 >> 24);
+        a[4] = (float)(v1 & 0xFFu); a[5] = (float)((v1 >> 8) & 0xFFu); a[6] = (float)((v1 >> 16) & 0xFFu); a[7] = (float)(v1 >> 24);
+        a[8] = (float)(v2 & 0xFFu); a[9] = (float)((v2 >> 8) & 0xFFu); a[10] = (float)((v2 >> 16) & 0xFFu);
+        if (j == 5) bc = (int)((v1 >> 8) & 0xFFu);
+        r[j] = gauss_row<true>(a, row_tail);
+    }
+    const float acc = gauss_col<true>(r[5], r[4], r[6], r[3], r[7], r[2], r[8], r[1], r[9], r[0], r[10], col_tail);
+    int mean = __float2int_rn(acc);
+    mean = mean < 0 ? 0 : (mean > 255 ? 255 : mean);
+    const int d = bc - mean;
+    const bool m_mask = (d > rc.t_mask) != rc.inv, m_mark = (d > rc.t_marker) != rc.inv;
+    const int wi = yy * rc.mw + (xx >> 5);
+    const uint32_t bit = 1u << (xx & 31);
+    if (m_mask) atomicOr(&rc.smask[wi], bit);
+    if (m_mark && rc.two) atomicOr(&rc.smask[rc.n_mask + wi], bit);
 }
 
 extern __shared__ __align__(16) unsigned char ysmr_fused_smem[];
@@ -154,49 +193,78 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     const uint32_t s_grey = s_base, s_rq = s_base, s_blur = s_base + g.off_blur, s_list = s_base + g.off_list;
     uint32_t *smask = reinterpret_cast<uint32_t *>(ysmr_fused_smem + g.off_mask);
     FusedMisc *misc = reinterpret_cast<FusedMisc *>(ysmr_fused_smem + g.off_misc);
-    const int mw = tw >> 5;                                       // mask words per tile row
+    const int lmw = g.ltw - 5, mw = 1 << lmw;                     // mask words per tile row
     const int n_mask = th * mw;
 
     for (int i = tid; i < 2 * n_mask; i += FT_THREADS) smask[i] = 0u;
     if (tid == 0) { misc->tmin = 0xFFFFu; misc->tmax = 0u; misc->count = 0u; }
 
-    // ---- 1a: grey tile.  Row r <-> virtual image row ty0 - 6 + r, byte c <-> virtual column tx0 - 12 + c; virtual positions
-    // outside the image hold the REFLECT_101 pixel (what cv2.GaussianBlur reads there).
+    // ---- 1a: grey tile.  Row r <-> virtual image row ty0 - 6 + r, byte c <-> virtual column tx0 - 12 + c.  The blur reads
+    // one pixel beyond the image (REFLECT_101: column -1 is column 1, column W is column W-2, same for rows); everything
+    // further out is never used, so out-of-image words are whole-word loads of the nearest image word with one byte moved.
+    // A thread owns one pair of words (8 pixels) of every n-th row: column clamps and byte selectors are per-thread constants.
     {
-        const int gwr = (tw + 24) >> 2;                           // words per row
+        const int npair = (tw + 24) >> 3;                         // word pairs per row
+        const int rstep = FT_THREADS / npair;
         const int n_rows = th + 12;
-        const int dr = FT_THREADS / gwr, dc = FT_THREADS - dr * gwr;
-        int r = tid / gwr, c4 = tid - r * gwr;
-        constexpr int U = 4;
-        while (r < n_rows) {
-            uint32_t raw[U][C == 3 ? 3 : 1];
-            int rr[U], cc[U];
-            bool fast[U];
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                rr[u] = r; cc[u] = c4;
-                const int vx = tx0 - 12 + 4 * c4;
-                fast[u] = r < n_rows && vx >= 0 && vx + 3 < W;
-                if (fast[u]) {
-                    const int gy = reflect101(ty0 - 6 + r, H);
-                    const uint32_t *q = reinterpret_cast<const uint32_t *>(frame + ((int64_t)gy * W + vx) * C);
-                    raw[u][0] = __ldg(q);
-                    if (C == 3) { raw[u][1] = __ldg(q + 1); raw[u][2] = __ldg(q + 2); }
-                }
-                c4 += dc; r += dr;
-                if (c4 >= gwr) { c4 -= gwr; ++r; }
+        const bool y_inside = ty0 - 6 >= 0 && ty0 + th + 6 <= H;
+        const int r0 = tid / npair, cp = tid - r0 * npair;
+        if (r0 < rstep) {
+            const int vxa = tx0 - 12 + 8 * cp, vxb = vxa + 4;
+            const int offa = min(max(vxa, 0), W - 4) * C, offb = min(max(vxb, 0), W - 4) * C;
+            const uint32_t sela = vxa == -4 ? 0x1210u : (vxa == W ? 0x3212u : 0x3210u);
+            const uint32_t selb = vxb == -4 ? 0x1210u : (vxb == W ? 0x3212u : 0x3210u);
+            const int64_t rowstride = (int64_t)W * C;
+            uint32_t so = s_grey + r0 * gp + 8 * cp;
+            auto load = [&](int r, uint32_t (&raw)[2][C == 3 ? 3 : 1]) {
+                int gy = ty0 - 6 + r;
+                if (!y_inside) gy = reflect101(gy, H);
+                const uint8_t *rowp = frame + gy * rowstride;
+                const uint32_t *qa = reinterpret_cast<const uint32_t *>(rowp + offa), *qb = reinterpret_cast<const uint32_t *>(rowp + offb);
+                raw[0][0] = __ldg(qa); raw[1][0] = __ldg(qb);
+                if (C == 3) { raw[0][1] = __ldg(qa + 1); raw[0][2] = __ldg(qa + 2); raw[1][1] = __ldg(qb + 1); raw[1][2] = __ldg(qb + 2); }
+            };
+            auto store = [&](const uint32_t (&raw)[2][C == 3 ? 3 : 1]) {
+                const uint32_t va = C == 3 ? grey4_of_bgr(raw[0][0], raw[0][1], raw[0][2]) : raw[0][0];
+                const uint32_t vb = C == 3 ? grey4_of_bgr(raw[1][0], raw[1][1], raw[1][2]) : raw[1][0];
+                asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(so), "r"(__byte_perm(va, va, sela)), "r"(__byte_perm(vb, vb, selb)));
+                so += rstep * gp;
+            };
+            // three rows in flight
+            int r = r0;
+            for (; r + 2 * rstep < n_rows; r += 3 * rstep) {
+                uint32_t x0[2][C == 3 ? 3 : 1], x1[2][C == 3 ? 3 : 1], x2[2][C == 3 ? 3 : 1];
+                load(r, x0); load(r + rstep, x1); load(r + 2 * rstep, x2);
+                store(x0); store(x1); store(x2);
             }
-#pragma unroll
-            for (int u = 0; u < U; ++u) {
-                if (rr[u] >= n_rows) break;
-                uint32_t v;
-                if (fast[u]) v = C == 3 ? grey4_of_bgr(raw[u][0], raw[u][1], raw[u][2]) : raw[u][0];
-                else v = grey_word_slow<C>(frame, W, reflect101(ty0 - 6 + rr[u], H), tx0 - 12 + 4 * cc[u]);
-                sts32(s_grey + rr[u] * gp + 4 * cc[u], v);
+            for (; r < n_rows; r += rstep) {
+                uint32_t x0[2][C == 3 ? 3 : 1];
+                load(r, x0); store(x0);
             }
         }
     }
     __syncthreads();
+
+    // L2 prefetch of the input of the tile that the CTA launched `prefetch_dist` CTAs later will read (roughly one wave
+    // ahead): by then its lines sit in L2 and phase 1a pays an L2 round trip instead of a DRAM one.
+    if (g.prefetch_dist > 0) {
+        int64_t nb = (int64_t)blockIdx.x + g.prefetch_dist;
+        if (nb < (int64_t)gridDim.x) {
+            const int ntx = (int)(nb % g.tiles_x); nb /= g.tiles_x;
+            const int nty = (int)(nb % g.tiles_y);
+            const int nf = (int)(nb / g.tiles_y);
+            const uint8_t *nfr = p.frames + (int64_t)nf * p.frame_stride;
+            const int x_lo = max(ntx * tw - 12, 0), x_hi = min(ntx * tw + tw + 12, W);
+            const int lines = ((x_hi - x_lo) * C + 127 + 127) >> 7;              // 128-byte lines per row (one spare for alignment)
+            const int total = (th + 12) * lines;
+            for (int i = tid; i < total; i += FT_THREADS) {
+                const int r = i / lines, l = i - r * lines;
+                const int gy = min(max(nty * th - 6 + r, 0), H - 1);
+                const uint8_t *a = nfr + ((int64_t)gy * W + x_lo) * C + 128 * l;
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
+            }
+        }
+    }
 
     // ---- 1b: blurred tile, same geometry: row rb <-> virtual row ty0 - 5 + rb = grey rows rb, rb+1, rb+2.  A thread owns 8
     // columns (blurred words 2cg+1, 2cg+2) of a chunk of rows; the vertical 1-2-1 slides through registers.
@@ -242,7 +310,7 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     if (p.dbg_grey || p.dbg_blurred) {
         const int64_t plane = (int64_t)H * W;
         for (int i = tid; i < tw * th; i += FT_THREADS) {
-            const int yy = i / tw, xx = i - yy * tw;
+            const int yy = i >> g.ltw, xx = i & (tw - 1);
             const int x = tx0 + xx, y = ty0 + yy;
             if (x < W && y < H) {
                 if (p.dbg_grey) p.dbg_grey[f * plane + (int64_t)y * W + x] = ysmr_fused_smem[(yy + 6) * gp + 12 + xx];
@@ -298,67 +366,116 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     const bool inv = p.inverted != 0;
     const int tmin = (int)misc->tmin, tmax = (int)misc->tmax;
     const int range = tmax - tmin;
-    int sh = 0;
-    while (((BH_SUM * range) >> sh) > 255) ++sh;                  // row-pass results must fit a byte
-    const int base_p = inv ? 255 - tmax : tmin;                   // minimum of the polarised bytes
+    const int sh = max(0, 24 - __clz(BH_SUM * range));            // smallest shift with (BH_SUM * range) >> sh <= 255
     const int acc_row = inv ? BH_SUM * tmax : -BH_SUM * tmin;     // start of the row chain: sum h (p - base_p) >= 0
     const int ka = inv ? (int)KAn : (int)KA, kb = inv ? (int)KBn : (int)KB, kc = inv ? (int)KCn : (int)KC;
     const int ka2 = inv ? (int)KA2n : (int)KA2, kb2 = inv ? (int)KB2n : (int)KB2, kc2 = inv ? (int)KC2n : (int)KC2;
+    const int nq2 = tw >> 2;                                      // row-pass bytes of pixel pair X live in column
+                                                                  // X/2 (X even) or nq2 + X/2 (X odd) of the rq array
 
-    // ---- 2a: row pass.  Task (q, ry): blurred tile row ry + 1 (image row ty0 - 4 + ry), pixels 8q .. 8q+7 -> four pair results
-    // rq[X][ry], X = 4q .. 4q+3, stored transposed (bytes along ry).  Lanes run along ry: conflict-free LDS.64 (gp / 8 odd)
-    // and byte stores into consecutive bytes.
+    // ---- 2a: row pass.  Task (q, G): pixels 8q .. 8q+7 of the four blurred rows ry = 4G .. 4G+3 (tile row ry + 1, image row
+    // ty0 - 4 + ry) -> four pair results X = 4q .. 4q+3 per row, shifted to a byte, the four rows of a pair as one word of the
+    // transposed array rq[col(X)][ry].  Lanes run along q: consecutive LDS.64.
     {
-        const int nry = th + 8, nq = tw >> 3;
-        const int n_tasks = nq * nry;
-        const int dq = FT_THREADS / nry, dry = FT_THREADS - dq * nry;
-        int q = tid / nry, ry = tid - q * nry;
-        for (int t = tid; t < n_tasks; t += FT_THREADS) {
-            const uint32_t a = s_blur + (ry + 1) * gp + 8 * q + 8;                // relative words 2q-1 .. 2q+2
-            const uint2 lo = lds64(a), hi = lds64(a + 8);
-            int r0 = dp4a_us(lo.x, ka, acc_row); r0 = dp4a_us(lo.y, kb, r0); r0 = dp4a_us(hi.x, kc, r0);
-            int r1 = dp4a_us(lo.x, ka2, acc_row); r1 = dp4a_us(lo.y, kb2, r1); r1 = dp4a_us(hi.x, kc2, r1);
-            int r2 = dp4a_us(lo.y, ka, acc_row); r2 = dp4a_us(hi.x, kb, r2); r2 = dp4a_us(hi.y, kc, r2);
-            int r3 = dp4a_us(lo.y, ka2, acc_row); r3 = dp4a_us(hi.x, kb2, r3); r3 = dp4a_us(hi.y, kc2, r3);
-            const uint32_t o = s_rq + (4 * q) * rp + ry;
-            sts8(o, (uint32_t)(r0 >> sh)); sts8(o + rp, (uint32_t)(r1 >> sh));
-            sts8(o + 2 * rp, (uint32_t)(r2 >> sh)); sts8(o + 3 * rp, (uint32_t)(r3 >> sh));
-            ry += dry; q += dq;
-            if (ry >= nry) { ry -= nry; ++q; }
+        const int lq = g.ltw - 3, nq = 1 << lq, nG = (th + 8) >> 2;
+        for (int t = tid; t < nq * nG; t += FT_THREADS) {
+            const int q = t & (nq - 1), G = t >> lq;
+            uint32_t a = s_blur + (4 * G + 1) * gp + 8 * q + 8;                   // relative words 2q-1 .. 2q+2
+            int r0[4], r1[4], r2[4], r3[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint2 lo = lds64(a), hi = lds64(a + 8);
+                a += gp;
+                r0[k] = dp4a_us(lo.x, ka, acc_row); r0[k] = dp4a_us(lo.y, kb, r0[k]); r0[k] = dp4a_us(hi.x, kc, r0[k]);
+                r1[k] = dp4a_us(lo.x, ka2, acc_row); r1[k] = dp4a_us(lo.y, kb2, r1[k]); r1[k] = dp4a_us(hi.x, kc2, r1[k]);
+                r2[k] = dp4a_us(lo.y, ka, acc_row); r2[k] = dp4a_us(hi.x, kb, r2[k]); r2[k] = dp4a_us(hi.y, kc, r2[k]);
+                r3[k] = dp4a_us(lo.y, ka2, acc_row); r3[k] = dp4a_us(hi.x, kb2, r3[k]); r3[k] = dp4a_us(hi.y, kc2, r3[k]);
+            }
+            // four results (< 2^16) -> four bytes (result >> sh < 256): two results per register as 16-bit fields, one shift
+            // (the low bits of the upper field fall into byte 1, which is dropped), bytes 0 and 2 of both registers
+            auto pack = [&](const int (&r)[4]) {
+                const uint32_t lo = __byte_perm((uint32_t)r[0], (uint32_t)r[1], 0x5410) >> sh;
+                const uint32_t hi = __byte_perm((uint32_t)r[2], (uint32_t)r[3], 0x5410) >> sh;
+                return __byte_perm(lo, hi, 0x6420);
+            };
+            const uint32_t o0 = pack(r0), o1 = pack(r1), o2 = pack(r2), o3 = pack(r3);
+            const uint32_t o = s_rq + (2 * q) * rp + 4 * G;
+            sts32(o, o0); sts32(o + nq2 * rp, o1); sts32(o + rp, o2); sts32(o + (nq2 + 1) * rp, o3);
         }
     }
     __syncthreads();
 
-    // ---- 2b: column pass + candidate test.  Task (X, m): pixel pair X, output rows 4m .. 4m+3 (two row pairs).  A pixel is
-    // certain background iff  p <= floor(base_p + t_q + 0.48 + L), L = (column sum << sh) / 65536.
+    RefineCtx rc;
+    rc.s_blur = s_blur; rc.gp = gp; rc.tw = tw; rc.ltw = g.ltw; rc.mw = mw; rc.n_mask = n_mask; rc.tx0 = tx0;
+    rc.row_tail_from = p.row_tail_from; rc.col_tail_from = p.col_tail_from; rc.t_mask = p.t_mask; rc.t_marker = p.t_marker;
+    rc.inv = inv; rc.two = p.marker_bits != nullptr; rc.smask = smask;
+    const int list_cap = g.list_cap;
+    auto push = [&](int idx) {
+        const uint32_t k = atomicAdd(&misc->count, 1u);
+        if ((int)k < list_cap) asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_list + 2 * k), "r"(idx));
+        else refine_px(rc, idx);                                  // list full (a tile that is mostly foreground): decide right away
+    };
+
+    // ---- 2b: column pass + candidate test.  Task (j, m): the four pixels 4j .. 4j+3 (pairs X = 2j, 2j+1) of output rows
+    // 4m .. 4m+3 (row pairs 2m, 2m+1).  With q = p - base_p (0 .. range) a pixel is certain background iff
+    //     q <= T,  T = floor(t_q + 0.48 + L),  L = (column sum << sh) / 65536.
+    // range <= 127 (any tile that is not saturated): byte-parallel test  q + A >= 128  <=>  q > T  with A = clamp(127 - T, 0, 128),
+    // and A comes straight out of the dot-product chain run with negated weights.
     {
-        const int nx = tw >> 1, nm = th >> 2;
-        const int c0 = ((base_p + g.t_q) * 65536 + 31457) >> sh;  // arithmetic shift: floor, i.e. towards "candidate"
+        const int lj = g.ltw - 2, nj = 1 << lj, nm = th >> 2;
         const int ts = 16 - sh;
-        const int n_tasks = nx * nm;
-        const int dm = FT_THREADS / nx, dX = FT_THREADS - dm * nx;
-        int m = tid / nx, X = tid - m * nx;
-        for (int t = tid; t < n_tasks; t += FT_THREADS) {
-            const int m_ = m, X_ = X;
-            X += dX; m += dm;
-            if (X >= nx) { X -= nx; ++m; }
-            const uint32_t a = s_rq + X_ * rp + 4 * m_;
-            const uint32_t w0 = lds32(a), w1 = lds32(a + 4), w2 = lds32(a + 8);
-            int la = dp4a_us(w0, (int)KA, c0); la = dp4a_us(w1, (int)KB, la); la = dp4a_us(w2, (int)KC, la);
-            int lb = dp4a_us(w0, (int)KA2, c0); lb = dp4a_us(w1, (int)KB2, lb); lb = dp4a_us(w2, (int)KC2, lb);
-            const int ta = la >> ts, tb = lb >> ts;
-            const int x = tx0 + 2 * X_;
-            if (x >= W) continue;                                 // (W is even: a pair is inside or outside)
-            const uint32_t ba = s_blur + (4 * m_ + 5) * gp + 12 + 2 * X_;
+        const int c0 = (g.t_q * 65536 + 31457) >> sh;             // arithmetic shift: floor, i.e. towards "candidate"
+        const bool swar = range <= 127;
+        const int c1 = (128 << ts) - 1 - c0;
+        const int sgn = inv ? -1 : 1;
+        const uint32_t cq = inv ? (uint32_t)tmax * 0x01010101u : 0u - (uint32_t)tmin * 0x01010101u;
+        for (int t = tid; t < nj * nm; t += FT_THREADS) {
+            const int j = t & (nj - 1), m = t >> lj;
+            if (tx0 + 4 * j >= W) continue;                       // (W % 4 == 0: a word is inside or outside)
+            const uint32_t a = s_rq + j * rp + 4 * m;
+            const uint32_t e0 = lds32(a), e1 = lds32(a + 4), e2 = lds32(a + 8);
+            const uint32_t d0 = lds32(a + nq2 * rp), d1 = lds32(a + nq2 * rp + 4), d2 = lds32(a + nq2 * rp + 8);
+            const uint32_t ba = s_blur + (4 * m + 5) * gp + 12 + 4 * j;
+            const int y0 = ty0 + 4 * m;
+            if (swar) {
+                int aa0 = dp4a_us(e0, (int)KAn, c1); aa0 = dp4a_us(e1, (int)KBn, aa0); aa0 = dp4a_us(e2, (int)KCn, aa0);
+                int ab0 = dp4a_us(e0, (int)KA2n, c1); ab0 = dp4a_us(e1, (int)KB2n, ab0); ab0 = dp4a_us(e2, (int)KC2n, ab0);
+                int aa1 = dp4a_us(d0, (int)KAn, c1); aa1 = dp4a_us(d1, (int)KBn, aa1); aa1 = dp4a_us(d2, (int)KCn, aa1);
+                int ab1 = dp4a_us(d0, (int)KA2n, c1); ab1 = dp4a_us(d1, (int)KB2n, ab1); ab1 = dp4a_us(d2, (int)KC2n, ab1);
+                aa0 = __vimin_s32_relu(aa0 >> ts, 128); ab0 = __vimin_s32_relu(ab0 >> ts, 128);
+                aa1 = __vimin_s32_relu(aa1 >> ts, 128); ab1 = __vimin_s32_relu(ab1 >> ts, 128);
+                const uint32_t A_top = __byte_perm((uint32_t)aa0, (uint32_t)aa1, 0x4400);     // rows 4m, 4m+1
+                const uint32_t A_bot = __byte_perm((uint32_t)ab0, (uint32_t)ab1, 0x4400);     // rows 4m+2, 4m+3
+                // z = q + A per byte; bit 7 set <=> candidate.  cq is folded into A; all four rows are tested with one branch.
+                const uint32_t ct = cq + A_top, cb = cq + A_bot;
+                const uint32_t z0 = (uint32_t)sgn * lds32(ba) + ct, z1 = (uint32_t)sgn * lds32(ba + gp) + ct;
+                const uint32_t z2 = (uint32_t)sgn * lds32(ba + 2 * gp) + cb, z3 = (uint32_t)sgn * lds32(ba + 3 * gp) + cb;
+                if ((z0 | z1 | z2 | z3) & 0x80808080u) {
+                    const uint32_t zz[4] = {z0, z1, z2, z3};
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const uint32_t v = lds16(ba + k * gp);
-                int p0 = (int)(v & 0xFFu), p1 = (int)(v >> 8);
-                if (inv) { p0 = 255 - p0; p1 = 255 - p1; }
-                const int tt = k < 2 ? ta : tb;
-                if ((p0 > tt || p1 > tt) && ty0 + 4 * m_ + k < H) {
-                    if (p0 > tt) { const uint32_t idx = atomicAdd(&misc->count, 1u); asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_list + 2 * idx), "r"((4 * m_ + k) * tw + 2 * X_)); }
-                    if (p1 > tt) { const uint32_t idx = atomicAdd(&misc->count, 1u); asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_list + 2 * idx), "r"((4 * m_ + k) * tw + 2 * X_ + 1)); }
+                    for (int k = 0; k < 4; ++k) {
+                        uint32_t z = zz[k] & 0x80808080u;
+                        if (y0 + k >= H) z = 0;
+                        while (z) {
+                            const int byte = (__ffs(z) - 1) >> 3;
+                            z &= z - 1;
+                            push((4 * m + k) * tw + 4 * j + byte);
+                        }
+                    }
+                }
+            } else {
+                // saturated tile (range of the blurred tile > 127): scalar compares
+                int la0 = dp4a_us(e0, (int)KA, c0); la0 = dp4a_us(e1, (int)KB, la0); la0 = dp4a_us(e2, (int)KC, la0);
+                int lb0 = dp4a_us(e0, (int)KA2, c0); lb0 = dp4a_us(e1, (int)KB2, lb0); lb0 = dp4a_us(e2, (int)KC2, lb0);
+                int la1 = dp4a_us(d0, (int)KA, c0); la1 = dp4a_us(d1, (int)KB, la1); la1 = dp4a_us(d2, (int)KC, la1);
+                int lb1 = dp4a_us(d0, (int)KA2, c0); lb1 = dp4a_us(d1, (int)KB2, lb1); lb1 = dp4a_us(d2, (int)KC2, lb1);
+                la0 >>= ts; lb0 >>= ts; la1 >>= ts; lb1 >>= ts;
+                for (int k = 0; k < 4; ++k) {
+                    if (y0 + k >= H) break;
+                    const uint32_t q4 = (uint32_t)sgn * lds32(ba + k * gp) + cq;
+                    const int t0 = k < 2 ? la0 : lb0, t1 = k < 2 ? la1 : lb1;
+                    for (int b = 0; b < 4; ++b)
+                        if ((int)((q4 >> (8 * b)) & 0xFFu) > (b < 2 ? t0 : t1)) push((4 * m + k) * tw + 4 * j + b);
                 }
             }
         }
@@ -367,46 +484,18 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
 
     // ---- 3: exact decisions of the candidates (OpenCV's float32 arithmetic, front_arith.cuh)
     {
-        const int n_cand = (int)misc->count;
+        const int n_cand = min((int)misc->count, list_cap);
         for (int i = tid; i < n_cand; i += FT_THREADS) {
             uint32_t idx;
             asm volatile("ld.shared.u16 %0, [%1];" : "=r"(idx) : "r"(s_list + 2 * i));
-            const int yy = (int)idx / tw, xx = (int)idx - yy * tw;
-            const int x = tx0 + xx;
-            const bool row_tail = x >= p.row_tail_from, col_tail = x >= p.col_tail_from;
-            const uint32_t a0 = s_blur + yy * gp + 12 + xx - 5;   // tile row yy + 5 - 5, byte column of x - 5
-            const uint32_t al = a0 & ~3u;
-            const uint32_t sel = 0x3210u + 0x1111u * (a0 & 3u);
-            float r[11];
-            int bc = 0;
-#pragma unroll
-            for (int j = 0; j < 11; ++j) {
-                const uint32_t ra = al + j * gp;
-                const uint32_t u0 = lds32(ra), u1 = lds32(ra + 4), u2 = lds32(ra + 8), u3 = lds32(ra + 12);
-                const uint32_t v0 = __byte_perm(u0, u1, sel), v1 = __byte_perm(u1, u2, sel), v2 = __byte_perm(u2, u3, sel);
-                float a[11];
-                a[0] = (float)(v0 & 0xFFu); a[1] = (float)((v0 >> 8) & 0xFFu); a[2] = (float)((v0 >> 16) & 0xFFu); a[3] = (float)(v0 >> 24);
-                a[4] = (float)(v1 & 0xFFu); a[5] = (float)((v1 >> 8) & 0xFFu); a[6] = (float)((v1 >> 16) & 0xFFu); a[7] = (float)(v1 >> 24);
-                a[8] = (float)(v2 & 0xFFu); a[9] = (float)((v2 >> 8) & 0xFFu); a[10] = (float)((v2 >> 16) & 0xFFu);
-                if (j == 5) bc = (int)((v1 >> 8) & 0xFFu);
-                r[j] = gauss_row<true>(a, row_tail);
-            }
-            const float acc = gauss_col<true>(r[5], r[4], r[6], r[3], r[7], r[2], r[8], r[1], r[9], r[0], r[10], col_tail);
-            int mean = __float2int_rn(acc);
-            mean = mean < 0 ? 0 : (mean > 255 ? 255 : mean);
-            const int d = bc - mean;
-            const bool m_mask = (d > p.t_mask) != inv, m_mark = (d > p.t_marker) != inv;
-            const int wi = yy * mw + (xx >> 5);
-            const uint32_t bit = 1u << (xx & 31);
-            if (m_mask) atomicOr(&smask[wi], bit);
-            if (m_mark && p.marker_bits) atomicOr(&smask[n_mask + wi], bit);
+            refine_px(rc, (int)idx);
         }
     }
     __syncthreads();
 
     // ---- 4: mask tiles -> HBM
     for (int i = tid; i < n_mask; i += FT_THREADS) {
-        const int yy = i / mw, wx = i - yy * mw;
+        const int yy = i >> lmw, wx = i & (mw - 1);
         const int y = ty0 + yy, word = (tx0 >> 5) + wx;
         if (y < H && word < p.ww) {
             const int64_t o = ((int64_t)f * H + y) * p.ww + word;
@@ -424,8 +513,11 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
 static FusedGeom fused_geometry(const FrontParams &p)
 {
     FusedGeom g{};
-    g.tw = 256; g.th = 64;
-    if (p.w <= 128) g.tw = 128;
+    g.tw = p.w <= 128 ? 128 : 256; g.ltw = p.w <= 128 ? 7 : 8;
+    static int th_env = -1;                                       // YSMR_FUSED_TH: tile height override (tuning runs)
+    if (th_env < 0) { const char *e = getenv("YSMR_FUSED_TH"); th_env = e ? atoi(e) : 0; }
+    g.th = th_env > 0 ? th_env : 88;
+    if (p.h < g.th) g.th = (p.h + 3) & ~3;
     g.tiles_x = (p.w + g.tw - 1) / g.tw; g.tiles_y = (p.h + g.th - 1) / g.th;
     g.gp = g.tw + 24;
     while (g.gp % 8 != 0 || (g.gp / 8) % 2 == 0) g.gp += 4;
@@ -434,15 +526,19 @@ static FusedGeom fused_geometry(const FrontParams &p)
     const bool two = p.marker_bits != nullptr;
     if (!p.inverted) g.t_q = two ? (p.t_mask < p.t_marker ? p.t_mask : p.t_marker) : p.t_mask;
     else g.t_q = -(two ? (p.t_mask > p.t_marker ? p.t_mask : p.t_marker) : p.t_mask) - 1;
+    // shared memory: [grey tile | later: row-pass bytes, then the candidate list] [blurred tile] [mask tiles] [misc]
     const int grey_bytes = (g.th + 12) * g.gp, rq_bytes = (g.tw / 2) * g.rp;
-    const int list_off = (rq_bytes + 15) & ~15, list_bytes = 2 * g.tw * g.th;
-    int region_a = grey_bytes > list_off + list_bytes ? grey_bytes : list_off + list_bytes;
-    region_a = (region_a + 15) & ~15;
-    g.off_list = list_off;
+    g.off_list = (rq_bytes + 15) & ~15;
+    int region_a = (grey_bytes + 15) & ~15;
+    if (region_a < g.off_list + 4096) region_a = g.off_list + 4096;
+    g.list_cap = (region_a - g.off_list) / 2;
     g.off_blur = region_a;
     g.off_mask = g.off_blur + (((g.th + 10) * g.gp + 15) & ~15);
     g.off_misc = g.off_mask + 2 * g.th * (g.tw / 32) * 4;
     g.smem_bytes = g.off_misc + 16;
+    static int pf_env = -1;                                       // YSMR_FUSED_PF: prefetch distance override (tuning runs)
+    if (pf_env < 0) { const char *e = getenv("YSMR_FUSED_PF"); pf_env = e ? atoi(e) : 444; }
+    g.prefetch_dist = pf_env;
     return g;
 }
 
