@@ -35,8 +35,6 @@
 #include "frontend.cuh"
 #include "front_arith.cuh"
 
-#include <stdlib.h>
-
 namespace ysmr {
 
 constexpr int FT_THREADS = 256;
@@ -49,7 +47,6 @@ struct FusedGeom {
     int t_q;                    // polarised decision threshold (see fused_geometry)
     int off_blur, off_mask, off_list, off_misc;   // shared-memory offsets (bytes); grey tile and row-pass bytes at 0
     int list_cap;               // candidate list entries
-    int prefetch_dist;          // L2 prefetch distance in CTAs (0: off)
     int smem_bytes;
 };
 
@@ -230,41 +227,31 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
                 asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(so), "r"(__byte_perm(va, va, sela)), "r"(__byte_perm(vb, vb, selb)));
                 so += rstep * gp;
             };
-            // three rows in flight
+            // software pipeline: the loads of the next three rows are issued before the current three are converted
+            typedef uint32_t Raw[2][C == 3 ? 3 : 1];
+            Raw x0, x1, x2, y0, y1, y2;
             int r = r0;
-            for (; r + 2 * rstep < n_rows; r += 3 * rstep) {
-                uint32_t x0[2][C == 3 ? 3 : 1], x1[2][C == 3 ? 3 : 1], x2[2][C == 3 ? 3 : 1];
-                load(r, x0); load(r + rstep, x1); load(r + 2 * rstep, x2);
-                store(x0); store(x1); store(x2);
-            }
-            for (; r < n_rows; r += rstep) {
-                uint32_t x0[2][C == 3 ? 3 : 1];
-                load(r, x0); store(x0);
+            const int step3 = 3 * rstep;
+            auto load3 = [&](int rr, Raw &a, Raw &b, Raw &c) {
+                if (rr < n_rows) load(rr, a);
+                if (rr + rstep < n_rows) load(rr + rstep, b);
+                if (rr + 2 * rstep < n_rows) load(rr + 2 * rstep, c);
+            };
+            auto store3 = [&](int rr, const Raw &a, const Raw &b, const Raw &c) {
+                if (rr < n_rows) store(a);
+                if (rr + rstep < n_rows) store(b);
+                if (rr + 2 * rstep < n_rows) store(c);
+            };
+            load3(r, x0, x1, x2);
+            for (; r < n_rows; r += 2 * step3) {
+                load3(r + step3, y0, y1, y2);
+                store3(r, x0, x1, x2);
+                load3(r + 2 * step3, x0, x1, x2);
+                store3(r + step3, y0, y1, y2);
             }
         }
     }
     __syncthreads();
-
-    // L2 prefetch of the input of the tile that the CTA launched `prefetch_dist` CTAs later will read (roughly one wave
-    // ahead): by then its lines sit in L2 and phase 1a pays an L2 round trip instead of a DRAM one.
-    if (g.prefetch_dist > 0) {
-        int64_t nb = (int64_t)blockIdx.x + g.prefetch_dist;
-        if (nb < (int64_t)gridDim.x) {
-            const int ntx = (int)(nb % g.tiles_x); nb /= g.tiles_x;
-            const int nty = (int)(nb % g.tiles_y);
-            const int nf = (int)(nb / g.tiles_y);
-            const uint8_t *nfr = p.frames + (int64_t)nf * p.frame_stride;
-            const int x_lo = max(ntx * tw - 12, 0), x_hi = min(ntx * tw + tw + 12, W);
-            const int lines = ((x_hi - x_lo) * C + 127 + 127) >> 7;              // 128-byte lines per row (one spare for alignment)
-            const int total = (th + 12) * lines;
-            for (int i = tid; i < total; i += FT_THREADS) {
-                const int r = i / lines, l = i - r * lines;
-                const int gy = min(max(nty * th - 6 + r, 0), H - 1);
-                const uint8_t *a = nfr + ((int64_t)gy * W + x_lo) * C + 128 * l;
-                asm volatile("prefetch.global.L2 [%0];" ::"l"(a));
-            }
-        }
-    }
 
     // ---- 1b: blurred tile, same geometry: row rb <-> virtual row ty0 - 5 + rb = grey rows rb, rb+1, rb+2.  A thread owns 8
     // columns (blurred words 2cg+1, 2cg+2) of a chunk of rows; the vertical 1-2-1 slides through registers.
@@ -451,15 +438,22 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
                 const uint32_t z0 = (uint32_t)sgn * lds32(ba) + ct, z1 = (uint32_t)sgn * lds32(ba + gp) + ct;
                 const uint32_t z2 = (uint32_t)sgn * lds32(ba + 2 * gp) + cb, z3 = (uint32_t)sgn * lds32(ba + 3 * gp) + cb;
                 if ((z0 | z1 | z2 | z3) & 0x80808080u) {
-                    const uint32_t zz[4] = {z0, z1, z2, z3};
+                    // one slot reservation for all candidates of the task, then plain stores
+                    uint32_t zz[4] = {z0 & 0x80808080u, z1 & 0x80808080u, z2 & 0x80808080u, z3 & 0x80808080u};
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) if (y0 + k >= H) zz[k] = 0;
+                    const int n = __popc(zz[0]) + __popc(zz[1]) + __popc(zz[2]) + __popc(zz[3]);
+                    uint32_t slot = n ? atomicAdd(&misc->count, (uint32_t)n) : 0u;
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        uint32_t z = zz[k] & 0x80808080u;
-                        if (y0 + k >= H) z = 0;
+                        uint32_t z = zz[k];
                         while (z) {
                             const int byte = (__ffs(z) - 1) >> 3;
                             z &= z - 1;
-                            push((4 * m + k) * tw + 4 * j + byte);
+                            const int idx = (4 * m + k) * tw + 4 * j + byte;
+                            if ((int)slot < list_cap) asm volatile("st.shared.u16 [%0], %1;" ::"r"(s_list + 2 * slot), "r"(idx));
+                            else refine_px(rc, idx);
+                            ++slot;
                         }
                     }
                 }
@@ -485,7 +479,10 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     // ---- 3: exact decisions of the candidates (OpenCV's float32 arithmetic, front_arith.cuh)
     {
         const int n_cand = min((int)misc->count, list_cap);
-        for (int i = tid; i < n_cand; i += FT_THREADS) {
+        // candidate i goes to warp i % 8, lane (i / 8) % 32: a tile with a handful of candidates keeps all warps (and all
+        // four schedulers) busy instead of one
+        const int w = tid >> 5;
+        for (int i = w + 8 * lane; i < n_cand; i += FT_THREADS) {
             uint32_t idx;
             asm volatile("ld.shared.u16 %0, [%1];" : "=r"(idx) : "r"(s_list + 2 * i));
             refine_px(rc, (int)idx);
@@ -514,9 +511,9 @@ static FusedGeom fused_geometry(const FrontParams &p)
 {
     FusedGeom g{};
     g.tw = p.w <= 128 ? 128 : 256; g.ltw = p.w <= 128 ? 7 : 8;
-    static int th_env = -1;                                       // YSMR_FUSED_TH: tile height override (tuning runs)
-    if (th_env < 0) { const char *e = getenv("YSMR_FUSED_TH"); th_env = e ? atoi(e) : 0; }
-    g.th = th_env > 0 ? th_env : 88;
+    // tile height 104: the tallest tile with three CTAs per SM (71 KB of shared memory each); measured best of 56 .. 120 on
+    // 1228 x 922 (taller tiles amortise the 12-row halo and the per-phase set-up, shorter ones hide more latency)
+    g.th = 104;
     if (p.h < g.th) g.th = (p.h + 3) & ~3;
     g.tiles_x = (p.w + g.tw - 1) / g.tw; g.tiles_y = (p.h + g.th - 1) / g.th;
     g.gp = g.tw + 24;
@@ -536,9 +533,6 @@ static FusedGeom fused_geometry(const FrontParams &p)
     g.off_mask = g.off_blur + (((g.th + 10) * g.gp + 15) & ~15);
     g.off_misc = g.off_mask + 2 * g.th * (g.tw / 32) * 4;
     g.smem_bytes = g.off_misc + 16;
-    static int pf_env = -1;                                       // YSMR_FUSED_PF: prefetch distance override (tuning runs)
-    if (pf_env < 0) { const char *e = getenv("YSMR_FUSED_PF"); pf_env = e ? atoi(e) : 444; }
-    g.prefetch_dist = pf_env;
     return g;
 }
 
