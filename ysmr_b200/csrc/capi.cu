@@ -277,6 +277,10 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     CC(dev_alloc(c, &lx.flag, std::max(T, MB) + 2)); CC(dev_alloc(c, &lx.list, MB));
     lx.set_table_size = set_table_capacity((int)MB);
     CC(dev_alloc(c, &lx.table, (size_t)lx.set_table_size));
+    lx.prep_frames = 4096;
+    CC(dev_alloc(c, &lx.succ, (size_t)lx.prep_frames * 256));
+    CC(dev_alloc(c, &lx.thr2, (size_t)lx.prep_frames * 256));
+    lx.prep_margin = 2.0e-3f + 1.0e-6f * (float)(height + width);
     CC(dev_alloc(c, &c->phase_cycles, 16));
     CC(cudaMemset(c->phase_cycles, 0, 16 * sizeof(long long)));
     lx.phase_cycles = nullptr;
@@ -471,7 +475,8 @@ static int link_impl(ysmr_ctx *c, const int32_t *d_blob_count, const float *d_bl
     io.n_rows = (long long *)d_n_rows; io.append = append;
     io.status = &c->ctl->status; io.first_bad = &c->ctl->first_bad;
     ProfScope ps(c, YSMR_PROF_LINK, st);
-    CU(c, launch_link(c->lc, c->ls, c->lx, io, first_frame, n_frames, c->link_fast && c->gains_affine, st)); c->launches++;
+    CU(c, launch_link(c->lc, c->ls, c->lx, io, first_frame, n_frames, c->link_fast && c->gains_affine, st));
+    c->launches += (c->link_fast && c->gains_affine) ? 2 * ((n_frames + c->lx.prep_frames - 1) / c->lx.prep_frames) : 1;
     return YSMR_OK;
 }
 

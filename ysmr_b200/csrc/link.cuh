@@ -64,7 +64,12 @@ struct LinkScratch {
     int32_t *list;                       // [max_blobs] unused detections ascending, then in registration order
     int32_t *table;                      // [set_table_size] CPython set emulation
     int set_table_size;
-    long long *phase_cycles;             // [16] optional per-phase cycle counters of the fast path (NULL = off)
+    long long *phase_cycles;             // [16] (ABI 2 per-phase cycle counters; not maintained by the lane linker)
+    // candidate tables of the fast path, rebuilt per launch (link.cu: link_prep_kernel)
+    int32_t *succ;                       // [prep_frames][256] detection q of frame t -> nearest detection of frame t+1, or -1
+    float *thr2;                         // [prep_frames][256] squared acceptance radius of detection q of frame t
+    int prep_frames;                     // frames per sequential launch
+    float prep_margin;                   // float32 rounding bound of coordinates / distances (pixels)
 };
 
 struct RowOut {                          // must match ysmr_row (include/ysmr_b200.h)
