@@ -20,10 +20,9 @@ for rep in range(2):
     e0.record(); rows=ctx.link(counts,blobs,0,F*100); e1.record(); torch.cuda.synchronize()
     pc=ctx.link_phase_cycles()
     print('link ms', e0.elapsed_time(e1), 'rows', len(rows), 'frames', pc[12])
-    names=['dets+sync1','row minima','col winners','outcome+vote','predsum+row','mode+exp','total+div','out+push','estimate','-']
-    tot=sum(pc[:12])
-    for i in range(9): print('  %-20s %8.0f cyc/frame'%(names[i], pc[i]/max(pc[12],1)))
-    print('  total cyc/frame', sum(pc[:9])/max(pc[12],1))
+    names=['loop top + staging','candidate/scan/claim','barrier 2','conflict+outcome','barrier 4 (vote)','events','gsff','row + loop end']
+    for i in range(8): print('  %-22s %8.0f cyc/frame'%(names[i], pc[i]/max(pc[12],1)))
+    print('  total cyc/frame', sum(pc[:8])/max(pc[12],1), ' exact scans/frame', pc[8]/max(pc[12],1), ' conflict frames', pc[9], ' event frames', pc[10])
 # association regimes of the scene: n tracks (rows per frame) against m detections
 fr_ids = np.asarray(rows['frame']); npf = np.bincount(fr_ids, minlength=F)
 m = counts.cpu().numpy().astype(int)
