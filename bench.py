@@ -35,18 +35,64 @@ def parse():
     ap.add_argument('--steps', type=int, default=3)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
-    ap.add_argument('--frames', type=int, default=9000, help='frames per GPU (configs[1]: 9000)')
+    ap.add_argument('--config', default='cfg2', choices=['cfg2', 'cfg3', 'cfg4', 'cfg5'],
+                    help='BASELINE.json configuration (default cfg2 = configs[1], the one the metric is quoted on)')
+    ap.add_argument('--frames', type=int, default=0, help='frames per GPU (0: the default of the configuration)')
     ap.add_argument('--channels', type=int, default=3, choices=[1, 3])
-    ap.add_argument('--cells', type=int, default=50)
+    ap.add_argument('--cells', type=int, default=0, help='override the number of cells of the scene')
     ap.add_argument('--batch', type=int, default=0,
                     help='frames per detect launch (0: 1184 on one GPU, 592 = one chunk of the streamed hand-over on several)')
-    ap.add_argument('--cpu-frames', type=int, default=900, help='frames of the bounded CPU sample (about 15 s)')
+    ap.add_argument('--cpu-frames', type=int, default=0, help='frames of the bounded CPU sample (0: about 15 s for the configuration)')
     ap.add_argument('--e2e-frames', type=int, default=1000, help='frames in the pinned host buffer of the e2e leg')
     ap.add_argument('--multi', default='stream', choices=['stream', 'gather'],
                     help='N > 1: stream detection records chunk by chunk to the linker (default) or gather whole ranges')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--no-cpu', action='store_true')
-    return ap.parse_args()
+    args = ap.parse_args()
+    setup_config(args)
+    return args
+
+
+# ---- the BASELINE.json configurations ------------------------------------------------------------------------------------
+# frames: per GPU (cfg5: of the whole video, divided over the GPUs = strong scaling).  cfg3 / cfg4 run a prefix of the 9,000 /
+# 3,000 frames BASELINE names so that rendering the synthetic video and the default run stay within minutes; the prefix
+# length is part of config.workload.
+CONFIG_TABLE = {
+    'cfg2': dict(scene='cfg2', frames=9000, cpu_frames=900, max_blobs=128, max_tracks=1024, batch1=1184, white=True,
+                 what='cfg2: 1228x922, ~50 rods, default tracking.ini'),
+    'cfg3': dict(scene='cfg3', frames=592, cpu_frames=40, max_blobs=4096, max_tracks=8192, batch1=296, white=True,
+                 what='cfg3 (dense field): 1228x922, 2,000 rods/frame, adaptive double threshold 2.0'),
+    'cfg4': dict(scene='cfg4', frames=1480, cpu_frames=200, max_blobs=1024, max_tracks=4096, batch1=296, white=False,
+                 what='cfg4: 2048x2048, ~200 coccoid cells, dark on light'),
+    'cfg5': dict(scene='cfg2', frames=54000, cpu_frames=900, max_blobs=128, max_tracks=1024, batch1=1184, white=True,
+                 what='cfg5: one 54,000-frame 1228x922 video (cfg2 scene) sharded by frame range'),
+}
+
+
+def setup_config(args):
+    t = CONFIG_TABLE[args.config]
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    args.table = t
+    args.strong = args.config == 'cfg5'
+    if not args.frames:
+        args.frames = t['frames'] // world if args.strong else t['frames']
+    if not args.cpu_frames:
+        args.cpu_frames = t['cpu_frames']
+    args.white = t['white']
+
+
+def scene_config(args, n_total):
+    import dataclasses
+    from ysmr_b200.synth import CONFIGS
+    cfg = dataclasses.replace(CONFIGS[args.table['scene']], n_frames=n_total)
+    if args.cells:
+        cfg = dataclasses.replace(cfg, n_cells=args.cells)
+    return cfg
+
+
+def detect_settings(args):
+    from oracle import ref_stages
+    return ref_stages.DetectSettings(white_on_dark=args.white)
 
 
 # ---- clocks ------------------------------------------------------------------------------------------------------------
@@ -128,25 +174,61 @@ class ClockSampler:
 
 
 # ---- CPU baseline: the reference's loop body (oracle = cv2/scipy call sites + restated linker) ---------------------------
-def cpu_reference_fps(frames_bgr_or_grey, fps=30.0):
-    """Replays track_eval.py:180-316 on in-RAM frames (oracle/; the reference itself cannot travel to the GPU box)."""
+def cpu_reference_fps(frames_bgr_or_grey, st, fps=30.0, keep_rows=False):
+    """Replays track_eval.py:180-316 on in-RAM frames (oracle/; the reference itself cannot travel to the GPU box).
+    Returns (frames/s, seconds, rows or row count, cv2 threads); rows = [(frame, id, x, y, w, h, deg)]."""
     import cv2
     from oracle import ref_stages
     from oracle.tracker_port import LinkerPort
-    st = ref_stages.DetectSettings()
     lp = LinkerPort(max_disappeared=fps, fps=fps)
     t0 = time.perf_counter()
+    rows = []
     n_rows = 0
-    for f in frames_bgr_or_grey:
+    for t, f in enumerate(frames_bgr_or_grey):
         r = ref_stages.detect_frame(f, st)
-        n_rows += len(lp.update(r['rects']))
+        out = lp.update(r['rects'])
+        n_rows += len(out)
+        if keep_rows:
+            rows += [(t, i, xy[0], xy[1], info[0], info[1], info[2]) for (i, xy, info) in out]
     dt = time.perf_counter() - t0
-    return len(frames_bgr_or_grey) / dt, dt, n_rows, cv2.getNumThreads()
+    return len(frames_bgr_or_grey) / dt, dt, (np.array(rows, np.float64).reshape(-1, 7) if keep_rows else n_rows), cv2.getNumThreads()
 
 
 def scene_for(args, n_total):
-    from ysmr_b200.synth import SceneConfig, make_scene
-    return make_scene(SceneConfig(n_frames=n_total, n_cells=args.cells, seed=0))
+    from ysmr_b200.synth import make_scene
+    return make_scene(scene_config(args, n_total))
+
+
+def parity_check(gpu_rows, ref_rows):
+    """GPU rows of the first frames of the timed video against the oracle's rows of the same bytes (north_star bars): frame
+    and track id bit-exact; w/h/deg within 1e-3 (exact-area ties of cv2.minAreaRect are counted); x/y (GSFF)
+    within 1e-5 relative on EVERY row -- no exemption for coasting tracks: the device restates NumPy's roundings
+    (csrc/link.cuh), the fraction of rows whose float64 bits equal the oracle's is reported as well."""
+    out = {'frames': int(ref_rows[:, 0].max()) + 1 if len(ref_rows) else 0, 'rows': int(len(ref_rows)), 'rows_gpu': int(len(gpu_rows))}
+    if len(gpu_rows) != len(ref_rows):
+        out['ok'] = False
+        return out
+    ids_ok = bool((gpu_rows['frame'] == ref_rows[:, 0]).all() and (gpu_rows['track_id'] == ref_rows[:, 1]).all())
+    geo = np.stack([gpu_rows['w'], gpu_rows['h'], gpu_rows['deg']], 1).astype(np.float64)
+    gerr = np.abs(geo - ref_rows[:, 4:7].astype(np.float32)).max(1)
+    flips = int((gerr > 1e-3).sum())
+    err = np.maximum(np.abs(gpu_rows['x'] - ref_rows[:, 2]) / np.maximum(1, np.abs(ref_rows[:, 2])),
+                     np.abs(gpu_rows['y'] - ref_rows[:, 3]) / np.maximum(1, np.abs(ref_rows[:, 3])))
+    exact = (gpu_rows['x'] == ref_rows[:, 2]) & (gpu_rows['y'] == ref_rows[:, 3])
+    out.update({'ids_bit_exact': ids_ok, 'rect_max_err_excl_ties': float(gerr[gerr <= 1e-3].max()) if (gerr <= 1e-3).any() else 0.0,
+                'rect_area_tie_flips': flips, 'xy_rel_err_max_all_rows': float(err.max()) if len(err) else 0.0,
+                'xy_bit_exact_fraction': float(exact.mean()) if len(err) else 1.0})
+    # a tie flip moves one measurement by a fraction of a pixel and stays in that track's filter history: allow for it
+    bar = 1e-5 if flips == 0 else 1e-2
+    out['ok'] = bool(ids_ok and flips <= max(2, len(ref_rows) // 5000) and out['xy_rel_err_max_all_rows'] < bar)
+    return out
+
+
+def workload_text(args, channels, frames_per_gpu, world):
+    t = args.table
+    h, w = scene_config(args, 1).height, scene_config(args, 1).width
+    return (f'{t["what"]}; {w}x{h}x{channels} ({"BGR as cap.read() delivers" if channels == 3 else "grey plane"}), '
+            f'{frames_per_gpu} frames per GPU x {world} GPU(s)' + (' of one video (strong scaling)' if args.strong else ''))
 
 
 def run_reference(args):
@@ -159,22 +241,26 @@ def run_reference(args):
     scene = scene_for(args, n)
     grey = render_frames(scene, 0, n)
     frames = to_bgr(grey) if args.channels == 3 else grey
+    st = detect_settings(args)
     for _ in range(min(args.warmup, 1)):
-        cpu_reference_fps(frames[:30])
+        cpu_reference_fps(frames[:min(30, n)], st)
     vals, secs = [], []
     for _ in range(args.steps):
-        fps, dt, _, threads = cpu_reference_fps(frames)
+        fps, dt, _, threads = cpu_reference_fps(frames, st)
         vals.append(fps); secs.append(dt)
     v = float(np.mean(vals))
+    cfg = scene_config(args, 1)
     line = {
-        'impl': 'reference', 'metric': 'frames/sec detect+link at 1228x922', 'value': v, 'unit': 'frames/s',
+        'impl': 'reference', 'metric': f'frames/sec detect+link at {cfg.width}x{cfg.height}', 'value': v, 'unit': 'frames/s',
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': float(np.mean(secs) * 1000),
-        'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32/f64', 'data': 'synthetic',
-        'config': {'workload': f'cfg2 scene: 1228x922x{args.channels}, {args.cells} rods, default tracking.ini; '
-                               f'CPU sample = first {n} frames per step, frames in RAM'},
+        'higher_is_better': True, 'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'u8/f32/f64',
+        'data': 'synthetic',
+        'config': {'workload': workload_text(args, args.channels, args.frames, int(os.environ.get('WORLD_SIZE', '1'))) +
+                               f'; CPU sample = first {n} frames per step (numpy renderer, same scene), frames in RAM'},
         'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                          'sample': f'{n} frames/step x {args.steps} steps; oracle = the reference loop body '
-                                   f'(track_eval.py:180-316) on cv2/scipy + restated CentroidTracker/GSFF; '
+                                   f'(track_eval.py:180-316) on cv2/scipy + restated CentroidTracker/GSFF '
+                                   f'(speed of the restated tracker against the real class: BASELINE.md section 5); '
                                    f'host has {os.cpu_count()} cpus'},
         'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
@@ -187,6 +273,8 @@ def main():
     if args.impl == 'reference':
         return run_reference(args)
 
+    import hashlib
+
     import torch
     import torch.distributed as dist
     from ysmr_b200.api import ROW_DTYPE, Context
@@ -196,14 +284,17 @@ def main():
     rank = int(os.environ.get('RANK', '0'))
     local = int(os.environ.get('LOCAL_RANK', '0'))
     if not args.batch:
-        args.batch = 1184 if world == 1 else 592
+        args.batch = args.table['batch1'] if world == 1 else min(592, args.table['batch1'])
     assert torch.cuda.is_available(), 'bench.py needs a GPU (no CPU fallback)'
     torch.cuda.set_device(local)
     dev = torch.device('cuda', local)
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
 
-    H, W, Cn, F = 922, 1228, args.channels, args.frames
+    scfg = scene_config(args, 1)
+    H, W, Cn, F = scfg.height, scfg.width, args.channels, args.frames
+    if F * H * W * Cn > 170e9:
+        raise SystemExit(f'{args.config} with {F} frames of {H}x{W}x{Cn} per GPU does not fit one B200 (use --channels 1 or more GPUs)')
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, 'MEASURED_PEAKS.json')))
@@ -229,7 +320,7 @@ def main():
     n_local = sum(b - a for a, b in spans)
     shape = (n_local, H, W) if Cn == 1 else (n_local, H, W, 3)
     frames = torch.empty(shape, dtype=torch.uint8, device=dev)
-    G = 200
+    G = max(8, min(200, int(4e8 // (scfg.n_cells * 17 * 17 * 12 + H * W * 8))))   # frames per rendering call (memory bound)
     pos, span_pos = 0, []
     for a, b in spans:
         span_pos.append(pos)
@@ -239,9 +330,13 @@ def main():
             pos += y - x
     torch.cuda.synchronize()
 
-    MB, MT = 128, 1024              # capacities: detections per frame (the scene has ~50), live tracks
-    ctx = Context(H, W, Cn, local, max_batch=args.batch, max_blobs=MB, max_tracks=MT)
-    rows_cap = world * F * 160
+    MB, MT = args.table['max_blobs'], args.table['max_tracks']
+    ctx_kw = dict(max_blobs=MB, max_tracks=MT, white_on_dark=args.white)
+    if args.config == 'cfg3':
+        ctx_kw['max_runs'] = 65536
+    ctx = Context(H, W, Cn, local, max_batch=args.batch, **ctx_kw)
+    rows_per_frame = max(160, int(1.25 * scfg.n_cells))
+    rows_cap = world * F * rows_per_frame
     rows_buf = torch.empty(rows_cap * ROW_DTYPE.itemsize, dtype=torch.uint8, device=dev) if rank == 0 else None
 
     def step_single():
@@ -360,7 +455,7 @@ def main():
     for _ in range(max(args.warmup, 3)):
         step()
     barrier()
-    ctx.set_profiling(True)
+    # ---- timed region: no per-launch profiling (the per-kernel split comes from a separate pass below)
     launches0 = ctx.launch_count()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -376,13 +471,44 @@ def main():
     sampler.mark(1)
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
-    prof = ctx.get_profile()
-    ctx.set_profiling(False)
     launches = ctx.launch_count() - launches0
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    n_rows = int(n_rows_dev.item()) if rank == 0 else 0
+    rows = rows_dev[:n_rows * ROW_DTYPE.itemsize].cpu().numpy().view(ROW_DTYPE).copy() if rank == 0 else None
+
+    # ---- second, untimed pass with CUDA events around every launch: per-kernel times for the roofline block
+    ctx.set_profiling(True)
+    barrier()
+    step()
+    barrier()
+    prof = ctx.get_profile()
+    ctx.set_profiling(False)
+    prof_gen3 = None
+    if world == 1:
+        # the three-kernel front-end of round 1 on the same frames, for the A/B figure
+        ctx.set_option(ctx.OPT_FRONTEND_GEN, 3)
+        step(); torch.cuda.synchronize()
+        ctx.set_profiling(True)
+        step(); torch.cuda.synchronize()
+        prof_gen3 = ctx.get_profile()
+        ctx.set_profiling(False)
+        ctx.set_option(ctx.OPT_FRONTEND_GEN, 4)
+
+    # ---- multi-GPU identity: the streamed / gathered rows must be byte-identical to ONE sequential ysmr_link over the same
+    # detection records (different chunking of the linker, no streams, no NCCL in between)
+    multi_check = None
+    if stream_mode and rank == 0:
+        counts_all = torch.cat([chunk_views(chunk_buf[c], chunk_range(c)[1] - chunk_range(c)[0])[0] for c in range(n_chunks)])
+        blobs_all = torch.cat([chunk_views(chunk_buf[c], chunk_range(c)[1] - chunk_range(c)[0])[1] for c in range(n_chunks)])
+        ctx.reset()
+        rows_seq = ctx.link(counts_all.contiguous(), blobs_all.contiguous(), 0, rows_capacity=rows_cap)
+        multi_check = {'rows_sha256': hashlib.sha256(rows.tobytes()).hexdigest(),
+                       'sequential_link_sha256': hashlib.sha256(rows_seq.tobytes()).hexdigest()}
+        multi_check['identical'] = multi_check['rows_sha256'] == multi_check['sequential_link_sha256']
+        del counts_all, blobs_all
     if rank != 0:
         if world > 1:
             dist.barrier()
@@ -391,92 +517,107 @@ def main():
 
     total_frames = world * F * args.steps
     value = total_frames / (ms / 1000.0)
-    n_rows = int(n_rows_dev.item())
-    rows = rows_dev[:n_rows * ROW_DTYPE.itemsize].cpu().numpy().view(ROW_DTYPE)
     n_tracks = int(rows['track_id'].max()) + 1 if n_rows else 0
 
-    # ---- roofline: algorithmic bytes = H*W*C per frame (input read once), against the front-end launches that
-    # consume them (K1a blur pre-pass, K1b Gaussian + decisions -- the dominant kernel --, K1c mask packing), timed with
-    # CUDA events on the detection stream inside the timed region.  Per-kernel own DRAM traffic comes from the committed
-    # ncu capture (profiles/r1_traffic.json) when present.
+    # ---- roofline: algorithmic bytes = H*W*C per frame (input read once) against the front-end launch that
+    # consumes them -- fused_front_kernel (fused.cu), the dominant kernel -- timed with CUDA events on the detection stream.
+    # Its own DRAM traffic comes from the committed ncu capture (profiles/r2_traffic.json) when present.
     fe_ms, fe_n = prof['frontend']
     bytes_per_frame = H * W * Cn
-    frames_per_launch = (n_local * args.steps) / max(fe_n, 1)
+    frames_per_launch = n_local / max(fe_n, 1)
     per_launch_ms = fe_ms / max(fe_n, 1)
     achieved = (bytes_per_frame * frames_per_launch) / (per_launch_ms / 1000.0) / 1e9 if fe_ms > 0 else 0.0
     traffic = None
     try:
-        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r1_traffic.json')))
-        traffic = float(tj['frontend_dram_bytes_per_frame']) * frames_per_launch
+        tj = json.load(open(os.path.join(ROOT, 'profiles', 'r2_traffic.json')))
+        traffic = float(tj['frontend_dram_bytes_per_frame'][args.config]) * frames_per_launch
     except Exception:
         pass
-    kb = prof['k1b']
-    k1b_ms = kb[0] / max(kb[1], 1)
-    roofline = {'bound': 'hbm', 'kernel': 'front-end launches of one batch: K1a blur_prepass + margins, K1b gauss_decide (dominant), K1c pack_masks',
+    det_ms = prof['frontend'][0] + prof['label'][0] + prof['geometry'][0]
+    roofline = {'bound': 'hbm', 'kernel': 'fused_front_kernel (BGR -> grey -> blur -> adaptive double threshold -> bit masks, one launch per batch)',
                 'achieved': achieved, 'peak': hbm_peak, 'unit': 'GB/s', 'frac': achieved / hbm_peak, 'traffic': traffic,
                 'peak_source': peak_src, 'algorithmic_bytes_per_frame': bytes_per_frame, 'frames_per_launch': frames_per_launch,
                 'avg_launch_ms': per_launch_ms,
-                'dominant_kernel': {'name': 'gauss_decide_kernel (K1b)', 'avg_launch_ms': k1b_ms,
-                                    'share_of_frontend': kb[0] / fe_ms if fe_ms > 0 else None,
-                                    'note': 'issue-bound (FP32 + integer pipes), reads 1 B/px and writes 0.25 B/px; see DESIGN.md section 4'},
-                'kernel_ms_per_step': {k: v[0] / args.steps for k, v in prof.items()},
-                'whole_path_frac': (value * bytes_per_frame / 1e9) / (hbm_peak * world)}
+                'kernel_ms_per_step': {k: v[0] for k, v in prof.items() if v[1]},
+                'share_of_detection': prof['frontend'][0] / det_ms if det_ms > 0 else None,
+                'linker_us_per_frame': 1000.0 * prof['link'][0] / (world * F) if prof['link'][1] else None,
+                'whole_path_frac': (value * bytes_per_frame / 1e9) / (hbm_peak * world),
+                'note': 'per-kernel times from a separate profiled pass (CUDA events around every launch); value from the unprofiled timed region'}
+    if prof_gen3 is not None:
+        g3 = prof_gen3['frontend'][0]
+        roofline['three_kernel_frontend_of_round_1'] = {'ms_per_step': g3, 'frac': (bytes_per_frame * F / (g3 / 1000.0) / 1e9) / hbm_peak if g3 > 0 else None}
 
     # ---- e2e: the same metric through ysmr_track_host with pinned HOST frames (H2D + kernels + D2H rows inside) ---------
-    e2e = None
+    e2e = e2e_grey = None
     if not args.no_e2e and world == 1:
-        E = min(args.e2e_frames, F)
-        host = torch.empty((E,) + shape[1:], dtype=torch.uint8).pin_memory()
-        host.copy_(frames[:E])
-        host_np = host.numpy()
-        rows_out = np.empty(E * 160, ROW_DTYPE)
-        calls = (F + E - 1) // E
-        # host streaming uses the chunk size of the drop-in (ysmr_b200/track_eval.py): small chunks keep the H2D copy of chunk
-        # i+1 under the kernels of chunk i and the exposed tail short
-        ctx_e = Context(H, W, Cn, local, max_batch=256, max_blobs=MB, max_tracks=MT)
-        def e2e_step():
-            ctx_e.reset()
-            got = 0
-            for c in range(calls):
-                got += len(ctx_e.track_host(host_np, c * E, rows_capacity=len(rows_out), rows_out=rows_out))
-            return got
-        e2e_step()
-        torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        got = 0
-        for _ in range(args.steps):
-            got = e2e_step()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        e2e = {'value': calls * E * args.steps / dt, 'unit': 'frames/s',
-               'h2d_bytes_per_step': calls * E * bytes_per_frame, 'd2h_bytes_per_step': got * ROW_DTYPE.itemsize,
-               'note': f'ysmr_track_host on a pinned {E}-frame buffer x {calls} calls per step; wall clock incl. H2D, '
-                       f'kernels, D2H of rows'}
+        def e2e_leg(channels):
+            E = min(args.e2e_frames, F)
+            shp = (E, H, W) if channels == 1 else (E, H, W, 3)
+            host = torch.empty(shp, dtype=torch.uint8).pin_memory()
+            host.copy_(frames[:E] if channels == Cn else (frames[:E, :, :, 0] if Cn == 3 else frames[:E][..., None].expand(-1, -1, -1, 3)))
+            host_np = host.numpy()
+            rows_out = np.empty(E * rows_per_frame, ROW_DTYPE)
+            calls = (F + E - 1) // E
+            # host streaming uses the chunk size of the drop-in (ysmr_b200/track_eval.py): small chunks keep the H2D copy of
+            # chunk i+1 under the kernels of chunk i and the exposed tail short
+            ctx_e = Context(H, W, channels, local, max_batch=min(256, args.batch), **ctx_kw)
 
-    # ---- CPU baseline on a bounded sample of the same bytes ---------------------------------------------------------------
-    cpu = None
+            def e2e_step():
+                ctx_e.reset()
+                got = 0
+                for c in range(calls):
+                    got += len(ctx_e.track_host(host_np, c * E, rows_capacity=len(rows_out), rows_out=rows_out))
+                return got
+            e2e_step()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            got = 0
+            for _ in range(args.steps):
+                got = e2e_step()
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            ctx_e.close()
+            return {'value': calls * E * args.steps / dt, 'unit': 'frames/s',
+                    'h2d_bytes_per_step': calls * E * H * W * channels, 'd2h_bytes_per_step': got * ROW_DTYPE.itemsize,
+                    'note': f'ysmr_track_host on a pinned {E}-frame buffer of {channels}-channel frames x {calls} calls per step; '
+                            f'wall clock incl. H2D, kernels, D2H of rows'}
+        e2e = e2e_leg(Cn)
+        if Cn == 3:
+            # grey containers: the drop-in reads the decoder's single plane (cv2.CAP_PROP_CONVERT_RGB off) and opens the
+            # context with channels=1, so a third of the bytes cross PCIe (cv2.cvtColor is the identity when B == G == R)
+            e2e_grey = e2e_leg(1)
+
+    # ---- CPU baseline on a bounded sample of the same bytes, and the parity check of the timed bytes ----------------------
+    cpu = parity = None
     if not args.no_cpu and world == 1:
         S = min(args.cpu_frames, F)
         sample = frames[:S].cpu().numpy()
-        fps_cpu, dt_cpu, _, threads = cpu_reference_fps(sample)
+        fps_cpu, dt_cpu, ref_rows, threads = cpu_reference_fps(sample, detect_settings(args), keep_rows=True)
         cpu = {'value': fps_cpu, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                'sample': f'first {S} frames of the same video, {dt_cpu:.1f} s; reference loop body (track_eval.py:180-316) '
                          f'replayed on cv2/scipy + restated CentroidTracker/GSFF; host has {os.cpu_count()} cpus'}
+        parity = parity_check(rows[rows['frame'] < S], ref_rows)
 
     line = {
-        'metric': 'frames/sec detect+link at 1228x922', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
+        'metric': f'frames/sec detect+link at {W}x{H}', 'value': value, 'unit': 'frames/s', 'n_gpus': world,
         'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'u8/f32/f64', 'data': 'synthetic',
-        'config': {'workload': f'cfg2: 1228x922x{Cn} (BGR as cap.read() delivers) x {F} frames per GPU, {args.cells} rods, '
-                               f'default tracking.ini (white-on-dark, offset 5, adaptive double threshold 2.0, gsff 10/20/30)',
-                   'frames_per_gpu': F, 'batch': args.batch, 'l2': 'inputs (>= 10 GB) far exceed the 126 MB L2',
+        'scaling': 'strong' if args.strong else 'weak', 'vs_baseline': None, 'dtype': 'u8/f32/f64', 'data': 'synthetic',
+        'config': {'workload': workload_text(args, Cn, F, world) +
+                               f'; tracking.ini defaults (offset 5, adaptive double threshold 2.0, gsff 10/20/30), '
+                               f'{"white on dark" if args.white else "dark on light"}',
+                   'name': args.config, 'frames_per_gpu': F, 'batch': args.batch,
+                   'l2': f'inputs ({F * bytes_per_frame / 1e9:.1f} GB per GPU) far exceed the 126 MB L2',
                    'parallelism': (f'frame-range x{world}, one sequential linker' if not stream_mode else
                                    f'chunk-interleaved frame ranges x{world} ({B}-frame chunks, chunk c on rank c % {world}), '
                                    f'records streamed over NCCL to the one sequential linker on rank 0'),
-                   'rows': n_rows, 'tracks': n_tracks,
-                   'max_blobs': MB, 'max_tracks': MT},
+                   'rows': n_rows, 'tracks': n_tracks, 'max_blobs': MB, 'max_tracks': MT},
         'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+        'parity_check': parity,
     }
+    if e2e_grey is not None:
+        line['e2e_grey'] = e2e_grey
+    if multi_check is not None:
+        line['multi_gpu_check'] = multi_check
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()

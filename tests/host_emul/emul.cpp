@@ -136,8 +136,8 @@ struct HostLinker {
     LinkScratch x;
     std::vector<std::vector<double>> gains;
     std::vector<int32_t> hdr, order0, order1, free_slots, id, gone, mode, hist_n, hist_pos, col_row, row_arg, list, table;
-    std::vector<double> px, py, hist, wgt, xh, row_min, mom;
-    std::vector<int32_t> mom_ok;
+    std::vector<double> px, py, hist, wgt, xh, row_min;
+    double exp_tab[NP_EXP_TABLE];
     std::vector<float> iw, ih, ideg;
     std::vector<unsigned long long> col_best;
     std::vector<uint32_t> flag;
@@ -153,7 +153,7 @@ void *emul_link_create(double fps, int use_gsff, int n_f, const int32_t *n_i, co
     LinkConfig &c = L->c;
     c.max_disappeared = fps; c.max_distance = max_distance; c.use_gsff = use_gsff; c.n_f = n_f;
     c.max_tracks = max_tracks; c.max_blobs = max_blobs;
-    c.cross_zero = 1;
+    c.cross_zero = 1; c.xy_same = 1;
     const double *g = gain_full;
     L->gains.resize(n_f);
     for (int i = 0; i < n_f; ++i) {
@@ -166,11 +166,14 @@ void *emul_link_create(double fps, int use_gsff, int n_f, const int32_t *n_i, co
             L->gains[i][2 * n + k] = g[1 * 2 * n + 2 * k];
             L->gains[i][3 * n + k] = g[1 * 2 * n + 2 * k + 1];
             if (L->gains[i][n + k] != 0.0 || L->gains[i][2 * n + k] != 0.0) c.cross_zero = 0;
+            if (L->gains[i][k] != L->gains[i][3 * n + k]) c.xy_same = 0;
         }
         c.gain[i] = L->gains[i].data();
         g += 4 * 2 * n;
     }
     c.hist_len = use_gsff ? c.n_i[n_f - 1] + 1 : 1;
+    for (int k = 0; k < NP_EXP_TABLE; ++k) L->exp_tab[k] = d_from_bits(np_exp_table_bits(k));
+    c.exp_tab = L->exp_tab;
     const int T = max_tracks, B = max_blobs;
     L->hdr.assign(8, 0); L->order0.resize(T); L->order1.resize(T); L->free_slots.resize(T);
     L->id.assign(T, -1); L->gone.assign(T, 0); L->mode.assign(T, 0); L->hist_n.assign(T, 0); L->hist_pos.assign(T, 0);
@@ -183,8 +186,6 @@ void *emul_link_create(double fps, int use_gsff, int n_f, const int32_t *n_i, co
     s.id = L->id.data(); s.px = L->px.data(); s.py = L->py.data(); s.iw = L->iw.data(); s.ih = L->ih.data(); s.ideg = L->ideg.data();
     s.gone = L->gone.data(); s.mode = L->mode.data(); s.hist_n = L->hist_n.data(); s.hist_pos = L->hist_pos.data();
     s.hist = L->hist.data(); s.wgt = L->wgt.data(); s.xh = L->xh.data();
-    L->mom.resize((size_t)T * LINK_MAX_FILTERS * 4); L->mom_ok.assign(T, 0);
-    s.mom = L->mom.data(); s.mom_ok = L->mom_ok.data();
     L->col_best.resize(B); L->col_row.resize(B); L->row_min.resize(T); L->row_arg.resize(T);
     L->flag.resize((T > B ? T : B) + 2); L->list.resize(B); L->table.resize(set_table_capacity(B));
     LinkScratch &x = L->x;
@@ -207,6 +208,22 @@ int emul_link_chunk(void *h, const int32_t *blob_count, const float *blobs, int 
     HostLinkCta cta;
     link_chunk(cta, L->c, L->s, L->x, io, first_frame, n_frames);
     return status;
+}
+
+// numpy.exp restatement (link.cuh: np_exp_nonpos) on an array of non-positive arguments
+void emul_np_exp(const double *x, double *out, int n)
+{
+    double tab[NP_EXP_TABLE];
+    for (int k = 0; k < NP_EXP_TABLE; ++k) tab[k] = d_from_bits(np_exp_table_bits(k));
+    for (int i = 0; i < n; ++i) out[i] = np_exp_nonpos(x[i], tab);
+}
+
+// one row of numpy.dot(gain (rows x 2n), y (2n)) in the dgemv_t order (link.cuh: blas_row_dot); g_row = 2n doubles
+double emul_blas_row_dot(const double *g_row, const double *y, int n)
+{
+    std::vector<double> g0(n), g1(n);
+    for (int k = 0; k < n; ++k) { g0[k] = g_row[2 * k]; g1[k] = g_row[2 * k + 1]; }
+    return blas_row_dot(g0.data(), g1.data(), false, y, 0, n, n);
 }
 
 void emul_set_order(int32_t *keys, int n)

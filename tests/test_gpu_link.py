@@ -9,7 +9,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 torch = pytest.importorskip('torch')
 
-from tests.util import GOLDEN, coasting_age, pack_dets  # noqa: E402
+from tests.util import GOLDEN, pack_dets  # noqa: E402
 
 
 def _run(counts, blobs, use_gsff=True, chunk=10 ** 9, fps=30.0, max_tracks=2048, **kw):
@@ -30,11 +30,10 @@ def _check(got, rows):
     assert (got['frame'] == rows[:, 0]).all() and (got['track_id'] == rows[:, 1]).all()      # ids bit-exact
     for k, col in (('w', 4), ('h', 5), ('deg', 6)):
         assert (got[k] == rows[:, col].astype(np.float32)).all()
-    age = coasting_age(rows[:, 4:], rows[:, 1].astype(int))
-    err = np.maximum(np.abs(got['x'] - rows[:, 2]) / np.maximum(1, np.abs(rows[:, 2])),
-                     np.abs(got['y'] - rows[:, 3]) / np.maximum(1, np.abs(rows[:, 3])))
-    assert err[age <= 8].max() < 1e-5, err[age <= 8].max()
-    return err.max()
+    # GSFF positions: the device restates the reference's NumPy roundings (csrc/link.cuh), so EVERY row -- coasting
+    # tracks included, no exemption -- carries the reference's float64 bits (north-star bar: 1e-5 relative)
+    assert (got['x'] == rows[:, 2]).all() and (got['y'] == rows[:, 3]).all(), \
+        np.maximum(np.abs(got['x'] - rows[:, 2]), np.abs(got['y'] - rows[:, 3])).max()
 
 
 @pytest.mark.parametrize('path', sorted(glob.glob(os.path.join(GOLDEN, 'link_*.npz'))), ids=os.path.basename)

@@ -47,6 +47,7 @@ def load_cstages():
 def load_emul():
     lib = ctypes.CDLL(build_emul())
     lib.emul_link_create.restype = ctypes.c_void_p
+    lib.emul_blas_row_dot.restype = ctypes.c_double
     return lib
 
 

@@ -48,7 +48,6 @@ struct ysmr_ctx {
     int img_is_marker = 0;        // DIRECT on the marker image (dark-on-light quirk)
     int t_mask = 0, t_marker = 0, inverted = 0, signed_offset = 0;
     int window = 0;               // mean/std moving window (frames)
-    int gains_affine = 1;         // all uploaded FIR gains are affine in the tap index (required by the fast linker)
     int link_fast = 1;            // YSMR_LINK=general disables the shared-memory fast path of the linker (tests)
     int frontend_gen = 4;         // 3: force the three-kernel front-end (ysmr_set_option, A/B measurements in bench.py)
     cudaStream_t s_tail = nullptr; cudaEvent_t ev_tail_fork = nullptr, ev_tail_join = nullptr;   // K1b tail-strip launch
@@ -71,6 +70,7 @@ struct ysmr_ctx {
     LinkScratch lx{};
     long long *phase_cycles = nullptr;
     double *gain_dev[LINK_MAX_FILTERS] = {nullptr, nullptr, nullptr, nullptr};
+    double *exp_tab_dev = nullptr;
     bool gain_set[LINK_MAX_FILTERS] = {false, false, false, false};
     std::vector<std::pair<void *, size_t>> state_parts;   // for export/import
     // pipeline (ysmr_track_*)
@@ -240,7 +240,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     LinkConfig &lc = c->lc;
     lc.max_disappeared = params->fps; lc.max_distance = params->max_distance;
     lc.use_gsff = params->use_gsff; lc.n_f = params->use_gsff ? params->n_f : 0;
-    lc.max_tracks = params->max_tracks; lc.max_blobs = params->max_blobs; lc.cross_zero = 1;
+    lc.max_tracks = params->max_tracks; lc.max_blobs = params->max_blobs; lc.cross_zero = 1; lc.xy_same = 1;
     if (params->use_gsff) {
         const double step = (double)(params->n_max - params->n_min) / (double)params->n_f;      // gsff.py:103-106
         for (int i = 0; i < params->n_f; ++i) {
@@ -269,7 +269,6 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     CC(part(&ls.gone, T)); CC(part(&ls.mode, T)); CC(part(&ls.hist_n, T)); CC(part(&ls.hist_pos, T));
     CC(part(&ls.hist, T * (size_t)lc.hist_len * 2));
     CC(part(&ls.wgt, T * LINK_MAX_FILTERS)); CC(part(&ls.xh, T * LINK_MAX_FILTERS * 2));
-    CC(part(&ls.mom, T * LINK_MAX_FILTERS * 4)); CC(part(&ls.mom_ok, T));
     for (auto &pr : c->state_parts) CC(cudaMemset(pr.first, 0, pr.second));
     LinkScratch &lx = c->lx;
     CC(dev_alloc(c, &lx.col_best, MB)); CC(dev_alloc(c, &lx.col_row, MB));
@@ -286,6 +285,13 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     lx.phase_cycles = nullptr;
     for (int i = 0; i < lc.n_f; ++i) CC(dev_alloc(c, &c->gain_dev[i], (size_t)4 * lc.n_i[i]));
     for (int i = 0; i < LINK_MAX_FILTERS; ++i) lc.gain[i] = c->gain_dev[i];
+    {
+        double tab[NP_EXP_TABLE];
+        for (int k = 0; k < NP_EXP_TABLE; ++k) { const unsigned long long u = np_exp_table_bits(k); memcpy(&tab[k], &u, 8); }
+        CC(dev_alloc(c, &c->exp_tab_dev, (size_t)NP_EXP_TABLE));
+        CC(cudaMemcpy(c->exp_tab_dev, tab, sizeof(tab), cudaMemcpyHostToDevice));
+        lc.exp_tab = c->exp_tab_dev;
+    }
     CC(launch_link_reset(ls, params->max_tracks, nullptr)); c->launches++;
     CC(cudaDeviceSynchronize());
     // pipeline objects
@@ -354,14 +360,7 @@ int ysmr_set_gsff_gain(ysmr_ctx *c, int filter, int horizon, const double *h_gai
         g[k] = h_gain[2 * k]; g[n + k] = h_gain[2 * k + 1];
         g[2 * n + k] = h_gain[2 * n + 2 * k]; g[3 * n + k] = h_gain[2 * n + 2 * k + 1];
         if (g[n + k] != 0.0 || g[2 * n + k] != 0.0) c->lc.cross_zero = 0;
-    }
-    // The linker's fast path evaluates the filter as alpha*S0 + beta*S1 (link.cu), which needs gains affine in the tap
-    // index.  The reference's gains are (one-step-ahead line fit); anything else falls back to the general path.
-    for (int arr = 0; arr < 4; arr += 3) {
-        const double *a = g.data() + (size_t)arr * n;
-        const double beta = n > 1 ? (a[n - 1] - a[0]) / (double)(n - 1) : 0.0;
-        for (int k = 0; k < n; ++k)
-            if (fabs(a[k] - (a[0] + beta * k)) > 1e-13 * (1.0 + fabs(a[k]))) c->gains_affine = 0;
+        if (g[k] != g[3 * n + k]) c->lc.xy_same = 0;      // (the fast linker loads one tap for both axes)
     }
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaMemcpy(c->gain_dev[filter], g.data(), sizeof(double) * g.size(), cudaMemcpyHostToDevice));
@@ -475,8 +474,8 @@ static int link_impl(ysmr_ctx *c, const int32_t *d_blob_count, const float *d_bl
     io.n_rows = (long long *)d_n_rows; io.append = append;
     io.status = &c->ctl->status; io.first_bad = &c->ctl->first_bad;
     ProfScope ps(c, YSMR_PROF_LINK, st);
-    CU(c, launch_link(c->lc, c->ls, c->lx, io, first_frame, n_frames, c->link_fast && c->gains_affine, st));
-    c->launches += (c->link_fast && c->gains_affine) ? 2 * ((n_frames + c->lx.prep_frames - 1) / c->lx.prep_frames) : 1;
+    CU(c, launch_link(c->lc, c->ls, c->lx, io, first_frame, n_frames, c->link_fast, st));
+    c->launches += (c->link_fast) ? 2 * ((n_frames + c->lx.prep_frames - 1) / c->lx.prep_frames) : 1;
     return YSMR_OK;
 }
 

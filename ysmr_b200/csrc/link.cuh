@@ -30,10 +30,12 @@ struct LinkConfig {
     int n_i[LINK_MAX_FILTERS];           // horizons (gsff.py:103-109)
     int hist_len;                        // n_i[n_f-1] + 1 (gsff.py:317-318)
     int cross_zero;                      // 1: the x<-y / y<-x gain entries are all exactly zero
+    int xy_same;                         // 1: the x and y rows of every gain carry identical taps
     // gains, device memory: for filter i four arrays of n_i[i] doubles: xx, xy, yx, yy
     //   x_hat = sum_k xx[k]*mx[k] + xy[k]*my[k] ; y_hat = sum_k yx[k]*mx[k] + yy[k]*my[k]
     const double *gain[LINK_MAX_FILTERS];
     int max_tracks, max_blobs;
+    const double *exp_tab;               // np_exp_table_bits as 32 doubles (device memory)
 };
 
 // Persistent linker state (device memory).  Tracks live in physical slots; `order` lists the slots in insertion order
@@ -50,8 +52,6 @@ struct LinkState {
     double *hist;                        //   [slot][hist_len][2]
     double *wgt;                         //   [slot][LINK_MAX_FILTERS]
     double *xh;                          //   [slot][LINK_MAX_FILTERS][2]
-    double *mom;                         //   [slot][LINK_MAX_FILTERS][4] window moments S0x,S0y,S1x,S1y (fast path cache)
-    int32_t *mom_ok;                     //   [slot] 1 while `mom` matches the history (only the fast path maintains it)
 };
 
 // Per-frame scratch (device: global memory owned by the context).
@@ -139,6 +139,124 @@ YSMR_HD void cpython_set_order(int32_t *keys, int n, int32_t *table)
         if (table[j] >= 0) keys[k++] = table[j];
 }
 
+// ---- float64 arithmetic with explicit rounding ----------------------------------------------------------------------
+// The GSFF recursion feeds its own output back while a track is unmatched, which amplifies a last-bit difference by
+// about 2.5x per frame: after a 30-frame coast anything but the reference's exact operation sequence is pixels away and
+// a different track wins the next contested detection.  So the filter below is not "the same formula", it is the same
+// ROUNDINGS as the reference's NumPy calls on x86-64 (verified bit for bit on the build host, tests/test_np_arith.py):
+//   * numpy.dot(gain (4 x 2n), y (2n))  -> OpenBLAS dgemv_t, Haswell kernel (used for every AVX2-or-later x86 target):
+//     four accumulators over the positions p = 0..2n-1 (p mod 4), each a chain of FMAs starting from +0, combined as
+//     (l0 + l2) + (l1 + l3); if 2n % 4 == 2 the last two positions are added as  + fma(a0, y0, a1 * y1).
+//   * numpy.dot(d, d) (2 elements)      -> fma(d1, d1, d0 * d0)
+//   * numpy.exp (float64, AVX-512)      -> SVML __svml_exp8_ha: restated in np_exp_nonpos below
+//   * sum(list * array), numpy.sum(axis=1) over <= 4 entries -> left to right, products rounded separately
+//   * a * b / c                         -> IEEE multiply, then IEEE divide
+#if defined(__CUDA_ARCH__)
+YSMR_D double d_mul(double a, double b) { return __dmul_rn(a, b); }
+YSMR_D double d_add(double a, double b) { return __dadd_rn(a, b); }
+YSMR_D double d_sub(double a, double b) { return __dsub_rn(a, b); }
+YSMR_D double d_fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+YSMR_D double d_fma_rz(double a, double b, double c) { return __fma_rz(a, b, c); }
+YSMR_D double d_div(double a, double b) { return __ddiv_rn(a, b); }
+YSMR_D double d_from_bits(unsigned long long u) { return __longlong_as_double((long long)u); }
+#else
+}  // namespace ysmr
+#include <fenv.h>
+#include <string.h>
+namespace ysmr {
+inline double d_mul(double a, double b) { return a * b; }
+inline double d_add(double a, double b) { return a + b; }
+inline double d_sub(double a, double b) { return a - b; }
+inline double d_fma(double a, double b, double c) { return fma(a, b, c); }
+inline double d_fma_rz(double a, double b, double c)
+{
+    const int old = fegetround();
+    fesetround(FE_TOWARDZERO);
+    volatile double va = a, vb = b, vc = c;
+    volatile double r = fma(va, vb, vc);
+    fesetround(old);
+    return r;
+}
+inline double d_div(double a, double b) { return a / b; }
+inline double d_from_bits(unsigned long long u) { double v; memcpy(&v, &u, 8); return v; }
+#endif
+
+// Table of the exp restatement: 2^(j/16) as high part and RELATIVE low part, j = 0..15 (32 doubles: hi[16], lo[16]).
+// Computed to the published construction (hi = 2^(j/16) rounded to nearest, lo = (2^(j/16) - hi) / hi) and checked
+// against numpy.exp over 10^6 arguments by tests/test_np_arith.py.
+constexpr int NP_EXP_TABLE = 32;
+YSMR_HD unsigned long long np_exp_table_bits(int k)
+{
+    constexpr unsigned long long t[NP_EXP_TABLE] = {
+        0x3ff0000000000000ull, 0x3ff0b5586cf9890full, 0x3ff172b83c7d517bull, 0x3ff2387a6e756238ull,
+        0x3ff306fe0a31b715ull, 0x3ff3dea64c123422ull, 0x3ff4bfdad5362a27ull, 0x3ff5ab07dd485429ull,
+        0x3ff6a09e667f3bcdull, 0x3ff7a11473eb0187ull, 0x3ff8ace5422aa0dbull, 0x3ff9c49182a3f090ull,
+        0x3ffae89f995ad3adull, 0x3ffc199bdd85529cull, 0x3ffd5818dcfba487ull, 0x3ffea4afa2a490daull,
+        0x0000000000000000ull, 0x3c979aa65d837b6dull, 0xbc801b15eaa59348ull, 0x3c968efde3a8a894ull,
+        0x3c834d754db0abb6ull, 0x3c859f48a72a4c6dull, 0x3c7690cebb7aafb0ull, 0x3c9063e1e21c5409ull,
+        0xbc93b3efbf5e2228ull, 0xbc7b32dcb94da51dull, 0x3c8db72fc1f0eab4ull, 0x3c71affc2b91ce27ull,
+        0x3c8c1a7792cb3387ull, 0x3c736eae30af0cb3ull, 0x3c74a385a63d07a7ull, 0xbc8ff7128fd391f0ull};
+    return t[k];
+}
+
+// numpy.exp(x) for -700 < x <= 0, float64, as NumPy >= 1.22 computes it on AVX-512 hosts: x = (k + j/16) ln2 + r with
+// (k + j/16) = x * log2(e) rounded TOWARD ZERO to a multiple of 1/16 (a fused multiply-add onto 1.5 * 2^48, whose low
+// mantissa bits then hold j), r = x - N ln2 with a two-part ln2, a degree-6 polynomial in a fixed FMA order, and
+// hi * (p * r + lo) + hi scaled by 2^k.  `tab` = the 32 doubles of np_exp_table_bits (shared or global memory).
+YSMR_HD double np_exp_nonpos(double x, const double *tab)
+{
+    const double shifter = d_from_bits(0x42f8000000003ff0ull);
+    const double z = d_fma_rz(x, d_from_bits(0x3ff71547652b82feull), shifter);
+    const double n = d_sub(z, shifter);
+    const int j = (int)(f64_bits(z) & 15ull);
+    double r = d_fma(-n, d_from_bits(0x3fe62e42fefa39efull), x);
+    r = d_fma(-n, d_from_bits(0x3c7abc9e3b39803full), r);
+    const double r2 = d_mul(r, r);
+    double p = d_fma(d_from_bits(0x3f57411836940c04ull), r, d_from_bits(0x3f81101cbbc265c0ull));
+    const double p9 = d_fma(d_from_bits(0x3fa55557242d68feull), r, d_from_bits(0x3fc5555553939732ull));
+    const double p11 = d_fma(d_from_bits(0x3fe000000000d008ull), r, d_from_bits(0x3fefffffffffff70ull));
+    p = d_fma(r2, p, p9);
+    p = d_fma(r2, p, p11);
+    const double q = d_fma(p, r, tab[16 + j]);
+    const double res = d_fma(tab[j], q, tab[j]);
+    const int k = (int)floor(n);                                 // n <= 0, a multiple of 1/16
+    return d_from_bits(f64_bits(res) + ((unsigned long long)(long long)k << 52));   // res in [1, 2), result normal
+}
+
+// gsff.py:179-202: likelihood of one filter, floor 1e-20.
+YSMR_HD double gsff_likelihood(double zx, double zy, double ex, double ey, const double *tab)
+{
+    const double dx = d_sub(zx, ex), dy = d_sub(zy, ey);
+    const double e = d_mul(-0.5, d_fma(dy, dy, d_mul(dx, dx)));
+    if (!(e > -47.0)) return 1e-20;                              // exp < 4e-21 (also catches NaN): the floor
+    const double v = np_exp_nonpos(e, tab);
+    return v < 1e-20 ? 1e-20 : v;
+}
+
+// One row of numpy.dot(gain_i, flattened history): g0 multiplies the x entries, g1 the y entries of the n newest
+// measurements (oldest first), in the dgemv_t order described above.  hist = ring of hist_len (x, y) pairs, j0 = index
+// of the oldest of the n.
+YSMR_HD double blas_row_dot(const double *g0, const double *g1, bool g1_zero, const double *hist, int j0, int hist_len, int n)
+{
+    double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
+    int j = j0;
+    const int nv = n & ~1;
+    for (int k = 0; k < nv; k += 2) {
+        const double ax = hist[2 * j], ay = hist[2 * j + 1];
+        if (++j == hist_len) j = 0;
+        const double bx = hist[2 * j], by = hist[2 * j + 1];
+        if (++j == hist_len) j = 0;
+        l0 = d_fma(g0[k], ax, l0); l2 = d_fma(g0[k + 1], bx, l2);
+        if (!g1_zero) { l1 = d_fma(g1[k], ay, l1); l3 = d_fma(g1[k + 1], by, l3); }
+    }
+    double r = d_add(d_add(l0, l2), d_add(l1, l3));
+    if (n & 1) {
+        const double ax = hist[2 * j], ay = hist[2 * j + 1];
+        r = d_add(r, d_fma(g0[n - 1], ax, g1_zero ? 0.0 : d_mul(g1[n - 1], ay)));
+    }
+    return r;
+}
+
 // ---- GSFF (gsff.py) for one track ----------------------------------------------------------------------------------
 
 YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot, int i);
@@ -156,6 +274,14 @@ YSMR_HD void gsff_push(const LinkConfig &c, const LinkState &s, int slot, double
     if (++pos == c.hist_len) pos = 0;
     s.hist_pos[slot] = pos;
     if (s.hist_n[slot] < c.hist_len) s.hist_n[slot] += 1;
+}
+
+// numpy.sum(x_hat_array * weight_array, axis=1) (gsff.py:242, 337): products rounded, summed left to right.
+YSMR_HD void gsff_weighted(const double *xh, const double *w, int mode, double *ox, double *oy)
+{
+    double fx = d_mul(xh[0], w[0]), fy = d_mul(xh[1], w[0]);
+    for (int i = 1; i < mode; ++i) { fx = d_add(fx, d_mul(xh[2 * i], w[i])); fy = d_add(fy, d_mul(xh[2 * i + 1], w[i])); }
+    *ox = fx; *oy = fy;
 }
 
 // GaussianSumFIR.correct (gsff.py:251-347) for one track: (zx, zy) = self.objects[key]; (ox, oy) = the filtered position
@@ -177,27 +303,19 @@ YSMR_HD void gsff_correct(const LinkConfig &c, const LinkState &s, int slot, dou
     double *xh = s.xh + (int64_t)slot * LINK_MAX_FILTERS * 2;
     if (switched) {
         s.mode[slot] = mode;
-        const double w0 = 1.0 / (double)mode;
+        const double w0 = d_div(1.0, (double)mode);  // 1 / mode * np.ones(mode)
         for (int i = 0; i < mode; ++i) w[i] = w0;
         gsff_estimates(c, s, slot, mode);
     }
-    double lik[LINK_MAX_FILTERS];
-    double total = 0.0;
+    double p[LINK_MAX_FILTERS];
+    double total = 0.0;                              // sum(likelihood_array * weight_array): 0 + p0 + p1 + ...
     for (int i = 0; i < mode; ++i) {
-        const double dx = zx - xh[2 * i], dy = zy - xh[2 * i + 1];
-        double v = exp(-0.5 * (dx * dx + dy * dy));
-        if (v < 1e-20) v = 1e-20;
-        lik[i] = v;
-        total = total + v * w[i];
+        p[i] = d_mul(gsff_likelihood(zx, zy, xh[2 * i], xh[2 * i + 1], c.exp_tab), w[i]);
+        total = d_add(total, p[i]);
     }
     gsff_push(c, s, slot, zx, zy);
-    double fx = 0.0, fy = 0.0;
-    for (int i = 0; i < mode; ++i) {
-        w[i] = lik[i] * w[i] / total;
-        if (i == 0) { fx = xh[0] * w[0]; fy = xh[1] * w[0]; }
-        else { fx = fx + xh[2 * i] * w[i]; fy = fy + xh[2 * i + 1] * w[i]; }
-    }
-    *ox = fx; *oy = fy;
+    for (int i = 0; i < mode; ++i) w[i] = d_div(p[i], total);
+    gsff_weighted(xh, w, mode, ox, oy);
 }
 
 // One least-squares FIR estimate (gsff.py:156-177, 230-240) of filter i for the predict step.
@@ -206,19 +324,12 @@ YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot
     const double *hist = s.hist + (int64_t)slot * c.hist_len * 2;
     const int n = c.n_i[i];
     const double *g = c.gain[i];
-    double ax = 0.0, ay = 0.0;
     int j = s.hist_pos[slot] - n; if (j < 0) j += c.hist_len;
-    for (int k = 0; k < n; ++k) {
-        const double mx = hist[2 * j], my = hist[2 * j + 1];
-        if (c.cross_zero) {
-            ax = fma(g[k], mx, ax);
-            ay = fma(g[3 * n + k], my, ay);
-        } else {
-            ax = fma(g[k], mx, ax); ax = fma(g[n + k], my, ax);
-            ay = fma(g[2 * n + k], mx, ay); ay = fma(g[3 * n + k], my, ay);
-        }
-        if (++j == c.hist_len) j = 0;
-    }
+    const bool cz = c.cross_zero != 0;
+    // row 0 of the gain: (xx, xy) on (x, y); row 1: (yx, yy).  With the reference's gains xy = yx = 0 exactly.
+    const double ax = blas_row_dot(g, g + n, cz, hist, j, c.hist_len, n);
+    const double ay = cz ? blas_row_dot(g + 3 * n, g + 3 * n, true, hist + 1, j, c.hist_len, n)
+                         : blas_row_dot(g + 2 * n, g + 3 * n, false, hist, j, c.hist_len, n);
     s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2] = ax;
     s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2 + 1] = ay;
 }
@@ -226,15 +337,8 @@ YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot
 // GaussianSumFIR.predict's weighted sum (gsff.py:242): the stored position becomes the prediction (tracker.py:225).
 YSMR_HD void gsff_combine(const LinkState &s, int slot)
 {
-    const int mode = s.mode[slot];
-    const double *w = s.wgt + (int64_t)slot * LINK_MAX_FILTERS;
-    const double *xh = s.xh + (int64_t)slot * LINK_MAX_FILTERS * 2;
-    double qx = 0.0, qy = 0.0;
-    for (int i = 0; i < mode; ++i) {
-        if (i == 0) { qx = xh[0] * w[0]; qy = xh[1] * w[0]; }
-        else { qx = qx + xh[2 * i] * w[i]; qy = qy + xh[2 * i + 1] * w[i]; }
-    }
-    s.px[slot] = qx; s.py[slot] = qy;
+    gsff_weighted(s.xh + (int64_t)slot * LINK_MAX_FILTERS * 2, s.wgt + (int64_t)slot * LINK_MAX_FILTERS, s.mode[slot],
+                  &s.px[slot], &s.py[slot]);
 }
 
 // correct() then predict() for one track (tracker.py:221-225), serial form used by the general path.
@@ -267,7 +371,6 @@ YSMR_HD void link_init_track(const LinkConfig &c, const LinkState &s, int slot, 
     s.iw[slot] = det[2]; s.ih[slot] = det[3]; s.ideg[slot] = det[4];
     s.gone[slot] = 0;
     s.mode[slot] = 0; s.hist_n[slot] = 0; s.hist_pos[slot] = 0;
-    s.mom_ok[slot] = 0;
 }
 
 // Processes frames [0, n_frames) of the chunk.  Header values live in registers of every thread and are updated
@@ -280,10 +383,6 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
     int n = s.hdr[0], next_id = s.hdr[1], n_free = s.hdr[2], sel = s.hdr[3];
     long long rows_total = io.append ? *io.n_rows : 0;
     bool row_overflow = false;
-    if (start_frame < n_frames) {          // this path does not maintain the fast path's moment cache
-        for (int r = tid; r < n; r += nthr) s.mom_ok[s.order[sel][r]] = 0;
-        cta.sync();
-    }
 
     for (int fi = start_frame; fi < n_frames; ++fi) {
         const int m = io.blob_count[fi];
