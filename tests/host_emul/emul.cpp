@@ -121,13 +121,10 @@ int emul_label(const uint8_t *mask, const uint8_t *markers, int h, int w, int ma
 #include "../../ysmr_b200/csrc/link.cuh"
 
 struct HostLinkCta : HostCta {
-    void atomic_min_u64(unsigned long long *p, unsigned long long v) const { if (v < *p) *p = v; }
+    unsigned long long atomic_min_u64(unsigned long long *p, unsigned long long v) const { const unsigned long long o = *p; if (v < o) *p = v; return o; }
     void atomic_min_i32(int32_t *p, int32_t v) const { if (v < *p) *p = v; }
-    void row_minima(const LinkConfig &c, const LinkState &s, const int32_t *order, int n, const float *dets, int m,
-                    double *row_min, int32_t *row_arg) const
-    {
-        row_minima_serial(*this, s, order, n, dets, m, row_min, row_arg);
-    }
+    uint32_t atomic_add_u32(uint32_t *p, uint32_t v) const { const uint32_t o = *p; *p = o + v; return o; }
+    bool any(int v) const { return v != 0; }
 };
 
 struct HostLinker {
@@ -135,7 +132,10 @@ struct HostLinker {
     LinkState s;
     LinkScratch x;
     std::vector<std::vector<double>> gains;
-    std::vector<int32_t> hdr, order0, order1, free_slots, id, gone, mode, hist_n, hist_pos, col_row, row_arg, list, table;
+    std::vector<int32_t> hdr, order0, order1, free_slots, id, gone, mode, hist_n, col_row, row_arg, list, table, cell_items, fflags;
+    std::vector<uint32_t> cell_start;
+    std::vector<float2> dxy;
+    FrameScratch f;
     std::vector<double> px, py, hist, wgt, xh, row_min;
     double exp_tab[NP_EXP_TABLE];
     std::vector<float> iw, ih, ideg;
@@ -154,6 +154,7 @@ void *emul_link_create(double fps, int use_gsff, int n_f, const int32_t *n_i, co
     c.max_disappeared = fps; c.max_distance = max_distance; c.use_gsff = use_gsff; c.n_f = n_f;
     c.max_tracks = max_tracks; c.max_blobs = max_blobs;
     c.cross_zero = 1; c.xy_same = 1;
+    c.grid_cell = 39.0; c.grid_w = 32; c.grid_h = 24;                  // what ysmr_create derives for 1228 x 922
     const double *g = gain_full;
     L->gains.resize(n_f);
     for (int i = 0; i < n_f; ++i) {
@@ -176,7 +177,7 @@ void *emul_link_create(double fps, int use_gsff, int n_f, const int32_t *n_i, co
     c.exp_tab = L->exp_tab;
     const int T = max_tracks, B = max_blobs;
     L->hdr.assign(8, 0); L->order0.resize(T); L->order1.resize(T); L->free_slots.resize(T);
-    L->id.assign(T, -1); L->gone.assign(T, 0); L->mode.assign(T, 0); L->hist_n.assign(T, 0); L->hist_pos.assign(T, 0);
+    L->id.assign(T, -1); L->gone.assign(T, 0); L->mode.assign(T, 0); L->hist_n.assign(T, 0);
     L->px.resize(T); L->py.resize(T); L->iw.resize(T); L->ih.resize(T); L->ideg.resize(T);
     L->hist.resize((size_t)T * c.hist_len * 2); L->wgt.resize((size_t)T * LINK_MAX_FILTERS); L->xh.resize((size_t)T * LINK_MAX_FILTERS * 2);
     for (int i = 0; i < T; ++i) L->free_slots[i] = T - 1 - i;
@@ -184,17 +185,26 @@ void *emul_link_create(double fps, int use_gsff, int n_f, const int32_t *n_i, co
     LinkState &s = L->s;
     s.hdr = L->hdr.data(); s.order[0] = L->order0.data(); s.order[1] = L->order1.data(); s.free_slots = L->free_slots.data();
     s.id = L->id.data(); s.px = L->px.data(); s.py = L->py.data(); s.iw = L->iw.data(); s.ih = L->ih.data(); s.ideg = L->ideg.data();
-    s.gone = L->gone.data(); s.mode = L->mode.data(); s.hist_n = L->hist_n.data(); s.hist_pos = L->hist_pos.data();
+    s.gone = L->gone.data(); s.mode = L->mode.data(); s.hist_n = L->hist_n.data();
     s.hist = L->hist.data(); s.wgt = L->wgt.data(); s.xh = L->xh.data();
     L->col_best.resize(B); L->col_row.resize(B); L->row_min.resize(T); L->row_arg.resize(T);
     L->flag.resize((T > B ? T : B) + 2); L->list.resize(B); L->table.resize(set_table_capacity(B));
     LinkScratch &x = L->x;
-    x.col_best = L->col_best.data(); x.col_row = L->col_row.data(); x.row_min = L->row_min.data(); x.row_arg = L->row_arg.data();
+    x.row_min = L->row_min.data(); x.row_arg = L->row_arg.data();
+    L->dxy.resize(B); L->cell_items.resize(B); L->cell_start.resize(LINK_GRID_CELLS + 2); L->fflags.assign(4, 0);
+    L->f.dxy = L->dxy.data(); L->f.col_best = L->col_best.data(); L->f.col_row = L->col_row.data();
+    L->f.cell_items = L->cell_items.data(); L->f.cell_start = L->cell_start.data(); L->f.flags = L->fflags.data();
     x.flag = L->flag.data(); x.list = L->list.data(); x.table = L->table.data(); x.set_table_size = (int)L->table.size();
     return L;
 }
 
 void emul_link_destroy(void *h) { delete (HostLinker *)h; }
+
+void emul_link_set_grid(void *h, double cell, int gw, int gh)
+{
+    HostLinker *L = (HostLinker *)h;
+    L->c.grid_cell = cell; L->c.grid_w = gw; L->c.grid_h = gh;
+}
 
 // blob_count[n_frames], blobs[n_frames][max_blobs][5]; rows as 5 doubles? -> RowOut array.  Returns status bits.
 int emul_link_chunk(void *h, const int32_t *blob_count, const float *blobs, int first_frame, int n_frames, void *rows,
@@ -206,7 +216,7 @@ int emul_link_chunk(void *h, const int32_t *blob_count, const float *blobs, int 
     io.blob_count = blob_count; io.blobs = blobs; io.rows = (RowOut *)rows; io.rows_capacity = rows_capacity;
     io.n_rows = n_rows; io.append = 0; io.status = &status; io.first_bad = &first_bad;
     HostLinkCta cta;
-    link_chunk(cta, L->c, L->s, L->x, io, first_frame, n_frames);
+    link_chunk(cta, L->c, L->s, L->x, L->f, io, first_frame, n_frames);
     return status;
 }
 
@@ -223,7 +233,7 @@ double emul_blas_row_dot(const double *g_row, const double *y, int n)
 {
     std::vector<double> g0(n), g1(n);
     for (int k = 0; k < n; ++k) { g0[k] = g_row[2 * k]; g1[k] = g_row[2 * k + 1]; }
-    return blas_row_dot(g0.data(), g1.data(), false, y, 0, n, n);
+    return blas_row_dot(g0.data(), g1.data(), false, y, 2, 0, n, n);
 }
 
 void emul_set_order(int32_t *keys, int n)

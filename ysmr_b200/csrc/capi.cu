@@ -68,6 +68,7 @@ struct ysmr_ctx {
     LinkConfig lc{};
     LinkState ls{};
     LinkScratch lx{};
+    FrameScratch lf{};
     long long *phase_cycles = nullptr;
     double *gain_dev[LINK_MAX_FILTERS] = {nullptr, nullptr, nullptr, nullptr};
     double *exp_tab_dev = nullptr;
@@ -266,12 +267,22 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     CC(part(&ls.order[0], T)); CC(part(&ls.order[1], T)); CC(part(&ls.free_slots, T));
     CC(part(&ls.id, T)); CC(part(&ls.px, T)); CC(part(&ls.py, T));
     CC(part(&ls.iw, T)); CC(part(&ls.ih, T)); CC(part(&ls.ideg, T));
-    CC(part(&ls.gone, T)); CC(part(&ls.mode, T)); CC(part(&ls.hist_n, T)); CC(part(&ls.hist_pos, T));
+    CC(part(&ls.gone, T)); CC(part(&ls.mode, T)); CC(part(&ls.hist_n, T));
     CC(part(&ls.hist, T * (size_t)lc.hist_len * 2));
     CC(part(&ls.wgt, T * LINK_MAX_FILTERS)); CC(part(&ls.xh, T * LINK_MAX_FILTERS * 2));
     for (auto &pr : c->state_parts) CC(cudaMemset(pr.first, 0, pr.second));
     LinkScratch &lx = c->lx;
-    CC(dev_alloc(c, &lx.col_best, MB)); CC(dev_alloc(c, &lx.col_row, MB));
+    FrameScratch &lf = c->lf;                  // general path: global-memory home of the per-frame scratch
+    CC(dev_alloc(c, &lf.col_best, MB)); CC(dev_alloc(c, &lf.col_row, MB)); CC(dev_alloc(c, &lf.dxy, MB));
+    CC(dev_alloc(c, &lf.cell_items, MB)); CC(dev_alloc(c, &lf.cell_start, (size_t)LINK_GRID_CELLS + 2)); CC(dev_alloc(c, &lf.flags, 4));
+    CC(dev_alloc(c, &lx.lane_done, 1));
+    CC(cudaMemset(lx.lane_done, 0, sizeof(int32_t)));
+    {
+        // detection grid of the general path: at most 32 x 32 cells of at least 16 pixels covering [0, W] x [0, H]
+        const int ext = (width > height ? width : height) + 1;
+        int cell = (ext + 31) / 32; if (cell < 16) cell = 16;
+        lc.grid_cell = (double)cell; lc.grid_w = width / cell + 1; lc.grid_h = height / cell + 1;
+    }
     CC(dev_alloc(c, &lx.row_min, T)); CC(dev_alloc(c, &lx.row_arg, T));
     CC(dev_alloc(c, &lx.flag, std::max(T, MB) + 2)); CC(dev_alloc(c, &lx.list, MB));
     lx.set_table_size = set_table_capacity((int)MB);
@@ -474,8 +485,8 @@ static int link_impl(ysmr_ctx *c, const int32_t *d_blob_count, const float *d_bl
     io.n_rows = (long long *)d_n_rows; io.append = append;
     io.status = &c->ctl->status; io.first_bad = &c->ctl->first_bad;
     ProfScope ps(c, YSMR_PROF_LINK, st);
-    CU(c, launch_link(c->lc, c->ls, c->lx, io, first_frame, n_frames, c->link_fast, st));
-    c->launches += (c->link_fast) ? 2 * ((n_frames + c->lx.prep_frames - 1) / c->lx.prep_frames) : 1;
+    CU(c, launch_link(c->lc, c->ls, c->lx, c->lf, io, first_frame, n_frames, c->link_fast, st));
+    c->launches += (c->link_fast) ? 3 * ((n_frames + c->lx.prep_frames - 1) / c->lx.prep_frames) : 1;
     return YSMR_OK;
 }
 

@@ -13,6 +13,7 @@
 #else
 #define YSMR_HD inline
 #define YSMR_D inline
+struct float2 { float x, y; };           // (host emulation only: the vector types come from cuda_runtime.h otherwise)
 #endif
 
 namespace ysmr {

@@ -36,6 +36,8 @@ struct LinkConfig {
     const double *gain[LINK_MAX_FILTERS];
     int max_tracks, max_blobs;
     const double *exp_tab;               // np_exp_table_bits as 32 doubles (device memory)
+    double grid_cell;                    // general path: cell size of the detection grid (pixels) ...
+    int grid_w, grid_h;                  // ... and its extent, grid_w * grid_h <= LINK_GRID_CELLS
 };
 
 // Persistent linker state (device memory).  Tracks live in physical slots; `order` lists the slots in insertion order
@@ -48,16 +50,14 @@ struct LinkState {
     double *px, *py;                     //   position used for the next association (GSFF prediction)
     float *iw, *ih, *ideg;               //   additional_info (w, h, deg) or zeros
     int32_t *gone;                       //   consecutive misses
-    int32_t *mode, *hist_n, *hist_pos;   //   GSFF: active filters, valid history entries, ring write position
-    double *hist;                        //   [slot][hist_len][2]
+    int32_t *mode, *hist_n;              //   GSFF: active filters, valid history entries
+    double *hist;                        //   [hist_len][max_tracks][2], row = frame counter mod hist_len
     double *wgt;                         //   [slot][LINK_MAX_FILTERS]
     double *xh;                          //   [slot][LINK_MAX_FILTERS][2]
 };
 
 // Per-frame scratch (device: global memory owned by the context).
 struct LinkScratch {
-    unsigned long long *col_best;        // [max_blobs] bits of the smallest row-minimum that chose this detection
-    int32_t *col_row;                    // [max_blobs] winning row
     double *row_min;                     // [max_tracks]
     int32_t *row_arg;                    // [max_tracks]
     uint32_t *flag;                      // [max(max_tracks, max_blobs) + 1] scan buffer
@@ -69,6 +69,7 @@ struct LinkScratch {
     int32_t *succ;                       // [prep_frames][256] detection q of frame t -> nearest detection of frame t+1, or -1
     float *thr2;                         // [prep_frames][256] squared acceptance radius of detection q of frame t
     int prep_frames;                     // frames per sequential launch
+    int32_t *lane_done;                  // [1] frames of the launch the fast path handled (read by link_general_kernel)
     float prep_margin;                   // float32 rounding bound of coordinates / distances (pixels)
 };
 
@@ -234,46 +235,51 @@ YSMR_HD double gsff_likelihood(double zx, double zy, double ex, double ey, const
 }
 
 // One row of numpy.dot(gain_i, flattened history): g0 multiplies the x entries, g1 the y entries of the n newest
-// measurements (oldest first), in the dgemv_t order described above.  hist = ring of hist_len (x, y) pairs, j0 = index
-// of the oldest of the n.
-YSMR_HD double blas_row_dot(const double *g0, const double *g1, bool g1_zero, const double *hist, int j0, int hist_len, int n)
+// measurements (oldest first), in the dgemv_t order described above.  hist = ring of hist_len (x, y) pairs `stride`
+// doubles apart, j0 = index of the oldest of the n.
+YSMR_HD double blas_row_dot(const double *g0, const double *g1, bool g1_zero, const double *hist, int64_t stride, int j0,
+                            int hist_len, int n)
 {
     double l0 = 0.0, l1 = 0.0, l2 = 0.0, l3 = 0.0;
     int j = j0;
     const int nv = n & ~1;
     for (int k = 0; k < nv; k += 2) {
-        const double ax = hist[2 * j], ay = hist[2 * j + 1];
+        const double ax = hist[j * stride], ay = g1_zero ? 0.0 : hist[j * stride + 1];
         if (++j == hist_len) j = 0;
-        const double bx = hist[2 * j], by = hist[2 * j + 1];
+        const double bx = hist[j * stride], by = g1_zero ? 0.0 : hist[j * stride + 1];
         if (++j == hist_len) j = 0;
         l0 = d_fma(g0[k], ax, l0); l2 = d_fma(g0[k + 1], bx, l2);
         if (!g1_zero) { l1 = d_fma(g1[k], ay, l1); l3 = d_fma(g1[k + 1], by, l3); }
     }
     double r = d_add(d_add(l0, l2), d_add(l1, l3));
     if (n & 1) {
-        const double ax = hist[2 * j], ay = hist[2 * j + 1];
+        const double ax = hist[j * stride], ay = g1_zero ? 0.0 : hist[j * stride + 1];
         r = d_add(r, d_fma(g0[n - 1], ax, g1_zero ? 0.0 : d_mul(g1[n - 1], ay)));
     }
     return r;
 }
 
 // ---- GSFF (gsff.py) for one track ----------------------------------------------------------------------------------
+// History ring: s.hist[(row * max_tracks + slot) * 2 + {0,1}], row = (frames linked so far) mod hist_len, the same row for
+// every track ("ring clock"); a track's hist_n newest rows are valid.
 
-YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot, int i);
+YSMR_HD double *gsff_hist_of(const LinkConfig &c, const LinkState &s, int slot) { return s.hist + 2 * (int64_t)slot; }
 
-YSMR_HD void gsff_estimates(const LinkConfig &c, const LinkState &s, int slot, int mode)
+// One least-squares FIR estimate (gsff.py:156-177, 230-240) of filter i over the n_i entries ending at row `newest`.
+YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot, int i, int newest)
 {
-    for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i);
-}
-
-YSMR_HD void gsff_push(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy)
-{
-    double *hist = s.hist + (int64_t)slot * c.hist_len * 2;
-    int pos = s.hist_pos[slot];
-    hist[2 * pos] = zx; hist[2 * pos + 1] = zy;
-    if (++pos == c.hist_len) pos = 0;
-    s.hist_pos[slot] = pos;
-    if (s.hist_n[slot] < c.hist_len) s.hist_n[slot] += 1;
+    const double *hist = gsff_hist_of(c, s, slot);
+    const int64_t stride = 2 * (int64_t)c.max_tracks;
+    const int n = c.n_i[i];
+    const double *g = c.gain[i];
+    int j = newest + 1 - n; if (j < 0) j += c.hist_len;
+    const bool cz = c.cross_zero != 0;
+    // row 0 of the gain: (xx, xy) on (x, y); row 1: (yx, yy).  With the reference's gains xy = yx = 0 exactly.
+    const double ax = blas_row_dot(g, g + n, cz, hist, stride, j, c.hist_len, n);
+    const double ay = cz ? blas_row_dot(g + 3 * n, g + 3 * n, true, hist + 1, stride, j, c.hist_len, n)
+                         : blas_row_dot(g + 2 * n, g + 3 * n, false, hist, stride, j, c.hist_len, n);
+    s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2] = ax;
+    s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2 + 1] = ay;
 }
 
 // numpy.sum(x_hat_array * weight_array, axis=1) (gsff.py:242, 337): products rounded, summed left to right.
@@ -284,17 +290,23 @@ YSMR_HD void gsff_weighted(const double *xh, const double *w, int mode, double *
     *ox = fx; *oy = fy;
 }
 
-// GaussianSumFIR.correct (gsff.py:251-347) for one track: (zx, zy) = self.objects[key]; (ox, oy) = the filtered position
-// that goes to the CSV.  Appends z to the history.
-YSMR_HD void gsff_correct(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy, double *ox, double *oy)
+// correct() then predict() for one track (tracker.py:221-225; gsff.py:251-347, 204-249): (zx, zy) = self.objects[key],
+// (ox, oy) = the filtered position that goes to the CSV; the stored position becomes the prediction.  `ring` = the row of
+// the current frame.
+YSMR_HD void gsff_step(const LinkConfig &c, const LinkState &s, int slot, int ring, double zx, double zy, double *ox, double *oy)
 {
-    if (s.hist_n[slot] == 0) {                       // first call: previous_measurements = [z] * n_i[0]
-        for (int k = 0; k < c.n_i[0]; ++k) gsff_push(c, s, slot, zx, zy);
+    double *hist = gsff_hist_of(c, s, slot);
+    const int64_t stride = 2 * (int64_t)c.max_tracks;
+    int hist_n = s.hist_n[slot];
+    if (hist_n == 0) {                               // first call: previous_measurements = [z] * n_i[0]
+        int e = ring - c.n_i[0]; if (e < 0) e += c.hist_len;
+        for (int k = 0; k < c.n_i[0]; ++k) { hist[e * stride] = zx; hist[e * stride + 1] = zy; if (++e == c.hist_len) e = 0; }
+        hist_n = c.n_i[0];
     }
     int mode = s.mode[slot];
     bool switched = false;
     if (mode < c.n_f) {
-        while (s.hist_n[slot] >= c.n_i[mode]) {
+        while (hist_n >= c.n_i[mode]) {
             ++mode; switched = true;
             if (mode >= c.n_f) break;
         }
@@ -305,7 +317,8 @@ YSMR_HD void gsff_correct(const LinkConfig &c, const LinkState &s, int slot, dou
         s.mode[slot] = mode;
         const double w0 = d_div(1.0, (double)mode);  // 1 / mode * np.ones(mode)
         for (int i = 0; i < mode; ++i) w[i] = w0;
-        gsff_estimates(c, s, slot, mode);
+        const int prev = ring == 0 ? c.hist_len - 1 : ring - 1;
+        for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i, prev);
     }
     double p[LINK_MAX_FILTERS];
     double total = 0.0;                              // sum(likelihood_array * weight_array): 0 + p0 + p1 + ...
@@ -313,41 +326,12 @@ YSMR_HD void gsff_correct(const LinkConfig &c, const LinkState &s, int slot, dou
         p[i] = d_mul(gsff_likelihood(zx, zy, xh[2 * i], xh[2 * i + 1], c.exp_tab), w[i]);
         total = d_add(total, p[i]);
     }
-    gsff_push(c, s, slot, zx, zy);
+    hist[ring * stride] = zx; hist[ring * stride + 1] = zy;
+    s.hist_n[slot] = hist_n < c.hist_len ? hist_n + 1 : hist_n;
     for (int i = 0; i < mode; ++i) w[i] = d_div(p[i], total);
     gsff_weighted(xh, w, mode, ox, oy);
-}
-
-// One least-squares FIR estimate (gsff.py:156-177, 230-240) of filter i for the predict step.
-YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot, int i)
-{
-    const double *hist = s.hist + (int64_t)slot * c.hist_len * 2;
-    const int n = c.n_i[i];
-    const double *g = c.gain[i];
-    int j = s.hist_pos[slot] - n; if (j < 0) j += c.hist_len;
-    const bool cz = c.cross_zero != 0;
-    // row 0 of the gain: (xx, xy) on (x, y); row 1: (yx, yy).  With the reference's gains xy = yx = 0 exactly.
-    const double ax = blas_row_dot(g, g + n, cz, hist, j, c.hist_len, n);
-    const double ay = cz ? blas_row_dot(g + 3 * n, g + 3 * n, true, hist + 1, j, c.hist_len, n)
-                         : blas_row_dot(g + 2 * n, g + 3 * n, false, hist, j, c.hist_len, n);
-    s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2] = ax;
-    s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2 + 1] = ay;
-}
-
-// GaussianSumFIR.predict's weighted sum (gsff.py:242): the stored position becomes the prediction (tracker.py:225).
-YSMR_HD void gsff_combine(const LinkState &s, int slot)
-{
-    gsff_weighted(s.xh + (int64_t)slot * LINK_MAX_FILTERS * 2, s.wgt + (int64_t)slot * LINK_MAX_FILTERS, s.mode[slot],
-                  &s.px[slot], &s.py[slot]);
-}
-
-// correct() then predict() for one track (tracker.py:221-225), serial form used by the general path.
-YSMR_HD void gsff_step(const LinkConfig &c, const LinkState &s, int slot, double zx, double zy, double *ox, double *oy)
-{
-    gsff_correct(c, s, slot, zx, zy, ox, oy);
-    const int mode = s.mode[slot];
-    for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i);
-    gsff_combine(s, slot);
+    for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i, ring);
+    gsff_weighted(xh, w, mode, &s.px[slot], &s.py[slot]);
 }
 
 // ---- one frame -------------------------------------------------------------------------------------------------------
@@ -370,19 +354,119 @@ YSMR_HD void link_init_track(const LinkConfig &c, const LinkState &s, int slot, 
     s.px[slot] = (double)det[0]; s.py[slot] = (double)det[1];
     s.iw[slot] = det[2]; s.ih[slot] = det[3]; s.ideg[slot] = det[4];
     s.gone[slot] = 0;
-    s.mode[slot] = 0; s.hist_n[slot] = 0; s.hist_pos[slot] = 0;
+    s.mode[slot] = 0; s.hist_n[slot] = 0;
 }
 
-// Processes frames [0, n_frames) of the chunk.  Header values live in registers of every thread and are updated
-// identically by all of them (every quantity they depend on is CTA-uniform), thread 0 writes them back at the end.
+// (s2_b, qb) beats (s2_a, qa) under "first index of the minimum ROUNDED distance" (numpy argmin over scipy's cdist row,
+// tracker.py:151-163).  Squared distances decide unless they are within 2^-50 relative, where the correctly rounded square
+// roots are compared -- so sqrt is almost never evaluated, yet the result is exactly the reference's.
+YSMR_HD bool nearer(double s2_a, int qa, double s2_b, int qb)
+{
+    const double eps = 8.8817841970012523e-16;   // 2^-50
+    if (s2_b < s2_a * (1.0 - eps)) return true;
+    if (s2_b > s2_a * (1.0 + eps)) return false;
+    const double da = sqrt(s2_a), db = sqrt(s2_b);
+    if (db != da) return db < da;
+    return qb < qa;
+}
+
+// Uniform grid over the detections of a frame (cells of `cell` pixels, gw x gh of them, coordinates clamped into it):
+// the exact nearest detection of a point is found by visiting the rings of cells around the point's cell until the best
+// distance found is provably smaller than the distance to anything not visited yet.  A clamped detection really lies
+// further out than its cell says, so the bound stays valid; a side of the visited square that has reached the edge of the
+// grid has nothing beyond it.
+struct DetGrid {
+    const float2 *dxy;                   // [m] detection centres
+    const uint32_t *cell_start;          // [gw*gh + 1]
+    const int32_t *cell_items;           // [m] detection indices grouped by cell
+    int gw, gh;
+    double cell, inv_cell;
+};
+
+YSMR_HD int grid_coord(double v, double inv_cell, int g)
+{
+    double t = floor(v * inv_cell);
+    t = fmax(t, 0.0);                    // (NaN -> 0)
+    t = fmin(t, (double)(g - 1));
+    return (int)t;
+}
+
+YSMR_HD void grid_visit(const DetGrid &G, int cx, int cy, double ox, double oy, double &best, int &arg)
+{
+    const int cidx = cy * G.gw + cx;
+    const uint32_t a = G.cell_start[cidx], b = G.cell_start[cidx + 1];
+    for (uint32_t t = a; t < b; ++t) {
+        const int q = G.cell_items[t];
+        const float2 d = G.dxy[q];
+        const double dx = d_sub(ox, (double)d.x), dy = d_sub(oy, (double)d.y);
+        const double s2 = d_add(d_mul(dx, dx), d_mul(dy, dy));      // scipy euclidean: s += d*d per coordinate
+        if (arg == 0x7fffffff || nearer(best, arg, s2, q)) { best = s2; arg = q; }
+    }
+}
+
+// first index of the minimum rounded distance over all m > 0 detections; *s2_out = its squared distance
+YSMR_HD int grid_nearest(const DetGrid &G, double ox, double oy, double *s2_out)
+{
+    const int cx = grid_coord(ox, G.inv_cell, G.gw), cy = grid_coord(oy, G.inv_cell, G.gh);
+    double best = 1.0e300; int arg = 0x7fffffff;
+    const int kmax = (G.gw > G.gh ? G.gw : G.gh);
+    for (int k = 0; k <= kmax; ++k) {
+        const int x0 = cx - k, x1 = cx + k, y0 = cy - k, y1 = cy + k;
+        if (k == 0) grid_visit(G, cx, cy, ox, oy, best, arg);
+        else {
+            const int xa = x0 < 0 ? 0 : x0, xb = x1 >= G.gw ? G.gw - 1 : x1;
+            if (y0 >= 0) for (int x = xa; x <= xb; ++x) grid_visit(G, x, y0, ox, oy, best, arg);
+            if (y1 < G.gh) for (int x = xa; x <= xb; ++x) grid_visit(G, x, y1, ox, oy, best, arg);
+            const int ya = y0 + 1 < 0 ? 0 : y0 + 1, yb = y1 - 1 >= G.gh ? G.gh - 1 : y1 - 1;
+            if (x0 >= 0) for (int y = ya; y <= yb; ++y) grid_visit(G, x0, y, ox, oy, best, arg);
+            if (x1 < G.gw) for (int y = ya; y <= yb; ++y) grid_visit(G, x1, y, ox, oy, best, arg);
+        }
+        // everything not visited yet lies outside the square of cells [x0, x1] x [y0, y1]
+        const bool L = x0 <= 0, R = x1 >= G.gw - 1, T = y0 <= 0, B = y1 >= G.gh - 1;
+        if (L && R && T && B) break;
+        if (arg != 0x7fffffff) {
+            double bound = 1.0e300;
+            if (!L) bound = fmin(bound, ox - (double)x0 * G.cell);
+            if (!R) bound = fmin(bound, (double)(x1 + 1) * G.cell - ox);
+            if (!T) bound = fmin(bound, oy - (double)y0 * G.cell);
+            if (!B) bound = fmin(bound, (double)(y1 + 1) * G.cell - oy);
+            // strictly nearer than anything outside, with room for the float32 coordinates and the roundings
+            if (bound > 0.0 && best < bound * bound * (1.0 - 1.0e-9)) break;
+        }
+    }
+    *s2_out = best;
+    return arg;
+}
+
+// Per-frame scratch of the general path: shared memory on the device when it fits, global memory otherwise; plain arrays in
+// the host emulation.
+struct FrameScratch {
+    float2 *dxy;                         // [max_blobs]
+    unsigned long long *col_best;        // [max_blobs] bits of the smallest row-minimum that chose this detection
+    int32_t *col_row;                    // [max_blobs] winning row (and scratch of the counting sort)
+    int32_t *cell_items;                 // [max_blobs]
+    uint32_t *cell_start;                // [LINK_GRID_CELLS + 2]
+    int32_t *flags;                      // [4]: 0 = some detection has two claimants at the same distance
+};
+
+constexpr int LINK_GRID_CELLS = 1024;    // at most 32 x 32 cells
+
+// Processes frames [start_frame, n_frames) of the chunk.  One CTA; within a frame the phases are loops over tracks or
+// detections separated by cta.sync().  Header values live in registers of every thread and are updated identically by all
+// of them (every quantity they depend on is CTA-uniform), thread 0 writes them back at the end.  Track state is
+// struct-of-arrays in global memory, the history ring entry-major ([row][slot], row = frame counter mod hist_len), so that
+// threads working on neighbouring slots touch neighbouring addresses.
 template <class Cta>
-YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const LinkScratch &x, const LinkIo &io,
-                        int first_frame, int n_frames, int start_frame = 0)
+YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const LinkScratch &x, const FrameScratch &f,
+                        const LinkIo &io, int first_frame, int n_frames, int start_frame = 0)
 {
     const int tid = cta.tid(), nthr = cta.nthr();
     int n = s.hdr[0], next_id = s.hdr[1], n_free = s.hdr[2], sel = s.hdr[3];
+    const int clock0 = s.hdr[4] - start_frame;   // frames linked before this launch: the ring clock (the fast path has
+                                                 // already counted the start_frame frames it handled)
     long long rows_total = io.append ? *io.n_rows : 0;
     bool row_overflow = false;
+    const int NONE = 0x7fffffff;
 
     for (int fi = start_frame; fi < n_frames; ++fi) {
         const int m = io.blob_count[fi];
@@ -400,25 +484,54 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
             for (int q = tid; q < m; q += nthr) x.list[q] = q;              // detection order (tracker.py:135-137)
             cta.sync();
         } else {
-            for (int q = tid; q < m; q += nthr) { x.col_best[q] = ~0ull; x.col_row[q] = 0x7fffffff; }
+            // ---- stage the detections and bin them into the grid (counting sort over cells)
+            DetGrid G;
+            G.dxy = f.dxy; G.cell_start = f.cell_start; G.cell_items = f.cell_items;
+            G.cell = c.grid_cell; G.inv_cell = 1.0 / c.grid_cell; G.gw = c.grid_w; G.gh = c.grid_h;
+            const int ncell = G.gw * G.gh;
+            for (int k = tid; k <= ncell; k += nthr) f.cell_start[k] = 0;
+            if (tid == 0) f.flags[0] = 0;
             cta.sync();
-            // nearest detection of every track (cdist row minimum / first argmin, tracker.py:151-163)
-            cta.row_minima(c, s, order, n, dets, m, x.row_min, x.row_arg);
-            cta.sync();
-            for (int r = tid; r < n; r += nthr) {
-                const double d = x.row_min[r];
-                if (c.max_distance <= 0.0 || d <= c.max_distance) cta.atomic_min_u64(&x.col_best[x.row_arg[r]], f64_bits(d));
+            for (int q = tid; q < m; q += nthr) {
+                float2 d; d.x = dets[5 * q]; d.y = dets[5 * q + 1];
+                f.dxy[q] = d;
+                f.col_best[q] = ~0ull;
+                const int cell = grid_coord((double)d.y, G.inv_cell, G.gh) * G.gw + grid_coord((double)d.x, G.inv_cell, G.gw);
+                x.flag[q] = (uint32_t)cell;
+                f.col_row[q] = (int32_t)cta.atomic_add_u32(&f.cell_start[cell], 1u);   // position within the cell
             }
             cta.sync();
-            for (int r = tid; r < n; r += nthr) {
-                const int q = x.row_arg[r];
-                if (x.col_best[q] == f64_bits(x.row_min[r]) && (c.max_distance <= 0.0 || x.row_min[r] <= c.max_distance))
-                    cta.atomic_min_i32(&x.col_row[q], r);
+            cta.exclusive_scan(f.cell_start, ncell + 1);
+            for (int q = tid; q < m; q += nthr) {
+                f.cell_items[f.cell_start[x.flag[q]] + (uint32_t)f.col_row[q]] = q;
+                f.col_row[q] = NONE;
             }
             cta.sync();
+            // ---- nearest detection of every track (cdist row minimum / first argmin, tracker.py:151-163) and its claim
+            for (int r = tid; r < n; r += nthr) {
+                const int slot = order[r];
+                double s2;
+                const int q = grid_nearest(G, s.px[slot], s.py[slot], &s2);
+                const double d = sqrt(s2);
+                x.row_min[r] = d; x.row_arg[r] = q;
+                if (c.max_distance <= 0.0 || d <= c.max_distance)
+                    if (cta.atomic_min_u64(&f.col_best[q], f64_bits(d)) == f64_bits(d)) f.flags[0] = 1;   // same distance twice
+            }
+            cta.sync();
+            // the smallest rounded distance wins a detection, the lowest row among equal distances (tracker.py:158-189)
+            const bool ties = f.flags[0] != 0;
+            if (ties) {
+                for (int r = tid; r < n; r += nthr) {
+                    const int q = x.row_arg[r];
+                    if (f.col_best[q] == f64_bits(x.row_min[r]) && (c.max_distance <= 0.0 || x.row_min[r] <= c.max_distance))
+                        cta.atomic_min_i32(&f.col_row[q], r);
+                }
+                cta.sync();
+            }
             for (int r = tid; r < n; r += nthr) {
                 const int q = x.row_arg[r];
-                const bool won = x.col_row[q] == r;
+                const bool ok = c.max_distance <= 0.0 || x.row_min[r] <= c.max_distance;
+                const bool won = ties ? f.col_row[q] == r : (ok && f.col_best[q] == f64_bits(x.row_min[r]));
                 x.flag[r] = won ? 1u : 0u;
                 if (won) {                                                  // tracker.py:181-184
                     const int slot = order[r];
@@ -426,13 +539,14 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
                     s.px[slot] = (double)d[0]; s.py[slot] = (double)d[1];
                     s.iw[slot] = d[2]; s.ih[slot] = d[3]; s.ideg[slot] = d[4];
                     s.gone[slot] = 0;
+                    if (!ties) f.col_row[q] = r;                            // marks the detection as used
                 }
             }
             cta.sync();
             if (n >= m) {
                 age_unmatched = true;                                       // tracker.py:198-211
             } else {                                                        // tracker.py:215-217
-                for (int q = tid; q <= m; q += nthr) x.flag[q] = (q < m && x.col_row[q] == 0x7fffffff) ? 1u : 0u;
+                for (int q = tid; q <= m; q += nthr) x.flag[q] = (q < m && f.col_row[q] == NONE) ? 1u : 0u;
                 cta.sync();
                 births = (int)cta.exclusive_scan(x.flag, m + 1);
                 for (int q = tid; q < m; q += nthr)
@@ -445,6 +559,7 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
 
         if (age_unmatched) {
             // flag[r] = 1 matched.  Age the others, drop those beyond max_disappeared, compact `order`.
+            int drop = 0;
             for (int r = tid; r < n; r += nthr) {
                 uint32_t keep = 1;
                 if (!x.flag[r]) {
@@ -452,14 +567,13 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
                     const int g = s.gone[slot] + 1;
                     s.gone[slot] = g;
                     s.iw[slot] = 0.f; s.ih[slot] = 0.f; s.ideg[slot] = 0.f;   // [0] * len(info)
-                    if ((double)g > c.max_disappeared) keep = 0;
+                    if ((double)g > c.max_disappeared) { keep = 0; drop = 1; }
                 }
                 x.flag[r] = keep;
             }
             if (tid == 0) x.flag[n] = 0;
-            cta.sync();
-            const int kept = (int)cta.exclusive_scan(x.flag, n + 1);
-            if (kept != n) {
+            if (cta.any(drop)) {                                            // (barrier + vote)
+                const int kept = (int)cta.exclusive_scan(x.flag, n + 1);
                 int32_t *order2 = s.order[sel ^ 1];
                 for (int r = tid; r < n; r += nthr) {
                     const int before = (int)x.flag[r];
@@ -490,10 +604,11 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
 
         // filter + emit (tracker.py:219-227, track_eval.py:313-316)
         const bool room = rows_total + n <= io.rows_capacity;
+        int ring = (clock0 + fi) % c.hist_len; if (ring < 0) ring += c.hist_len;
         for (int r = tid; r < n; r += nthr) {
             const int slot = order[r];
             double ox = s.px[slot], oy = s.py[slot];
-            if (c.use_gsff) gsff_step(c, s, slot, ox, oy, &ox, &oy);
+            if (c.use_gsff) gsff_step(c, s, slot, ring, ox, oy, &ox, &oy);
             if (room) {
                 RowOut &o = io.rows[rows_total + r];
                 o.frame = first_frame + fi; o.track_id = s.id[slot];
@@ -509,37 +624,16 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
     }
     if (tid == 0) {
         s.hdr[0] = n; s.hdr[1] = next_id; s.hdr[2] = n_free; s.hdr[3] = sel;
-        s.hdr[4] += n_frames - start_frame; s.hdr[5] = n;
+        s.hdr[4] = clock0 + (n_frames > start_frame ? n_frames : start_frame); s.hdr[5] = n;
         *io.n_rows = rows_total;
     }
 }
 
-// Row minima, generic one-thread-per-track form (the device policy overrides it with a multi-lane version).
-// scipy's euclidean: s = 0; s += d*d per coordinate (separately rounded); sqrt(s).  argmin = first index of the minimum
-// of the ROUNDED distances, so candidates whose squared distance is within a few ulp of the minimum are compared after
-// the square root.
-template <class Cta>
-YSMR_HD void row_minima_serial(const Cta &cta, const LinkState &s, const int32_t *order, int n, const float *dets, int m,
-                               double *row_min, int32_t *row_arg)
-{
-    for (int r = cta.tid(); r < n; r += cta.nthr()) {
-        const int slot = order[r];
-        const double ox = s.px[slot], oy = s.py[slot];
-        double best = 0.0; int arg = 0;
-        for (int q = 0; q < m; ++q) {
-            const double dx = ox - (double)dets[5 * q], dy = oy - (double)dets[5 * q + 1];
-            const double d = sqrt(dx * dx + dy * dy);
-            if (q == 0 || d < best) { best = d; arg = q; }
-        }
-        row_min[r] = best; row_arg[r] = arg;
-    }
-}
-
 #if defined(__CUDACC__)
-cudaError_t launch_link(const LinkConfig &c, const LinkState &s, const LinkScratch &x, const LinkIo &io, int first_frame,
-                        int n_frames, int allow_fast, cudaStream_t st);
+cudaError_t launch_link(const LinkConfig &c, const LinkState &s, const LinkScratch &x, const FrameScratch &f, const LinkIo &io,
+                        int first_frame, int n_frames, int allow_fast, cudaStream_t st);
 cudaError_t launch_link_reset(const LinkState &s, int max_tracks, cudaStream_t st);
-cudaError_t link_kernel_init();            // per device: shared-memory opt-in of link_kernel (from ysmr_create)
+cudaError_t link_kernel_init();            // per device: shared-memory opt-in of the linker kernels (from ysmr_create)
 #endif
 
 }  // namespace ysmr
