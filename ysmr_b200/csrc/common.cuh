@@ -10,9 +10,11 @@
 #if defined(__CUDACC__)
 #define YSMR_HD __host__ __device__ __forceinline__
 #define YSMR_D __device__ __forceinline__
+#define YSMR_HD_NOINLINE static __host__ __device__ __noinline__      // rare or bulky leaves: keep the callers' loop bodies small
 #else
 #define YSMR_HD inline
 #define YSMR_D inline
+#define YSMR_HD_NOINLINE inline
 struct float2 { float x, y; };           // (host emulation only: the vector types come from cuda_runtime.h otherwise)
 #endif
 

@@ -7,7 +7,7 @@
 namespace ysmr {
 
 constexpr int LABEL_THREADS = 256;
-constexpr int LINK_THREADS = 384;    // warps 0-3: one lane per track (fast path), warps 4-11: detection staging
+constexpr int LINK_THREADS = 512;    // warps 0-7: one lane per track (fast path), warps 8-15: detection staging + FIR helpers
 
 struct LabelLaunch {
     int n_frames, first_frame, h, w, ww, max_runs, max_blobs, mode_propagate;

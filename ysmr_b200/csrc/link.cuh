@@ -266,7 +266,7 @@ YSMR_HD double blas_row_dot(const double *g0, const double *g1, bool g1_zero, co
 YSMR_HD double *gsff_hist_of(const LinkConfig &c, const LinkState &s, int slot) { return s.hist + 2 * (int64_t)slot; }
 
 // One least-squares FIR estimate (gsff.py:156-177, 230-240) of filter i over the n_i entries ending at row `newest`.
-YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot, int i, int newest)
+YSMR_HD_NOINLINE void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot, int i, int newest)
 {
     const double *hist = gsff_hist_of(c, s, slot);
     const int64_t stride = 2 * (int64_t)c.max_tracks;
@@ -280,6 +280,66 @@ YSMR_HD void gsff_estimate_one(const LinkConfig &c, const LinkState &s, int slot
                          : blas_row_dot(g + 2 * n, g + 3 * n, false, hist, stride, j, c.hist_len, n);
     s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2] = ax;
     s.xh[((int64_t)slot * LINK_MAX_FILTERS + i) * 2 + 1] = ay;
+}
+
+// All active estimates of a track in ONE pass over its history (the general path's form of gsff_estimate_one for the
+// reference's gains: no x<->y coupling, identical x and y taps): every entry is loaded once and feeds each filter whose
+// horizon reaches back that far; the loads of six entries are issued before their multiply-adds so that their latencies
+// overlap.  Per filter and axis the same two FMA chains (even / odd taps, oldest first) as blas_row_dot; an odd horizon's
+// newest tap is the separately rounded tail.
+YSMR_HD void gsff_estimates_fused(const LinkConfig &c, const LinkState &s, int slot, int mode, int newest)
+{
+    const double *hist = gsff_hist_of(c, s, slot);
+    const int64_t stride = 2 * (int64_t)c.max_tracks;
+    const int L = c.hist_len;
+    int ni[LINK_MAX_FILTERS];
+#pragma unroll
+    for (int i = 0; i < LINK_MAX_FILTERS; ++i) ni[i] = i < mode ? c.n_i[i] : 0;
+    double ax[LINK_MAX_FILTERS][2], ay[LINK_MAX_FILTERS][2], tx[LINK_MAX_FILTERS], ty[LINK_MAX_FILTERS];
+#pragma unroll
+    for (int i = 0; i < LINK_MAX_FILTERS; ++i) { ax[i][0] = ax[i][1] = ay[i][0] = ay[i][1] = 0.0; tx[i] = ty[i] = 0.0; }
+    const int nmax = ni[mode - 1];
+    int e = newest - (nmax - 1); if (e < 0) e += L;
+    constexpr int B = 4;
+    for (int a0 = nmax - 1; a0 >= 0; a0 -= B) {
+        double vx[B], vy[B];
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            int eu = e + u; if (eu >= L) eu -= L;
+            const bool on = a0 - u >= 0;
+            vx[u] = on ? hist[eu * stride] : 0.0; vy[u] = on ? hist[eu * stride + 1] : 0.0;
+        }
+        e += B; if (e >= L) e -= L;
+#pragma unroll
+        for (int u = 0; u < B; ++u) {
+            const int a = a0 - u;
+#pragma unroll
+            for (int i = 0; i < LINK_MAX_FILTERS; ++i) {
+                if (a >= 0 && a < ni[i]) {
+                    const int k = ni[i] - 1 - a;
+                    const double g = c.gain[i][k];
+                    if (a == 0 && (ni[i] & 1)) { tx[i] = d_mul(g, vx[u]); ty[i] = d_mul(g, vy[u]); }
+                    else if (k & 1) { ax[i][1] = d_fma(g, vx[u], ax[i][1]); ay[i][1] = d_fma(g, vy[u], ay[i][1]); }
+                    else { ax[i][0] = d_fma(g, vx[u], ax[i][0]); ay[i][0] = d_fma(g, vy[u], ay[i][0]); }
+                }
+            }
+        }
+    }
+    double *xh = s.xh + (int64_t)slot * LINK_MAX_FILTERS * 2;
+#pragma unroll
+    for (int i = 0; i < LINK_MAX_FILTERS; ++i) {
+        if (i < mode) {
+            double rx = d_add(ax[i][0], ax[i][1]), ry = d_add(ay[i][0], ay[i][1]);
+            if (ni[i] & 1) { rx = d_add(rx, tx[i]); ry = d_add(ry, ty[i]); }
+            xh[2 * i] = rx; xh[2 * i + 1] = ry;
+        }
+    }
+}
+
+YSMR_HD void gsff_estimates(const LinkConfig &c, const LinkState &s, int slot, int mode, int newest)
+{
+    if (c.cross_zero && c.xy_same && c.hist_len >= 4) gsff_estimates_fused(c, s, slot, mode, newest);
+    else for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i, newest);
 }
 
 // numpy.sum(x_hat_array * weight_array, axis=1) (gsff.py:242, 337): products rounded, summed left to right.
@@ -318,7 +378,7 @@ YSMR_HD void gsff_step(const LinkConfig &c, const LinkState &s, int slot, int ri
         const double w0 = d_div(1.0, (double)mode);  // 1 / mode * np.ones(mode)
         for (int i = 0; i < mode; ++i) w[i] = w0;
         const int prev = ring == 0 ? c.hist_len - 1 : ring - 1;
-        for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i, prev);
+        gsff_estimates(c, s, slot, mode, prev);
     }
     double p[LINK_MAX_FILTERS];
     double total = 0.0;                              // sum(likelihood_array * weight_array): 0 + p0 + p1 + ...
@@ -330,7 +390,7 @@ YSMR_HD void gsff_step(const LinkConfig &c, const LinkState &s, int slot, int ri
     s.hist_n[slot] = hist_n < c.hist_len ? hist_n + 1 : hist_n;
     for (int i = 0; i < mode; ++i) w[i] = d_div(p[i], total);
     gsff_weighted(xh, w, mode, ox, oy);
-    for (int i = 0; i < mode; ++i) gsff_estimate_one(c, s, slot, i, ring);
+    gsff_estimates(c, s, slot, mode, ring);
     gsff_weighted(xh, w, mode, &s.px[slot], &s.py[slot]);
 }
 
@@ -360,13 +420,21 @@ YSMR_HD void link_init_track(const LinkConfig &c, const LinkState &s, int slot, 
 // (s2_b, qb) beats (s2_a, qa) under "first index of the minimum ROUNDED distance" (numpy argmin over scipy's cdist row,
 // tracker.py:151-163).  Squared distances decide unless they are within 2^-50 relative, where the correctly rounded square
 // roots are compared -- so sqrt is almost never evaluated, yet the result is exactly the reference's.
+// -1 / 0 / +1 for sqrt(a) <, ==, > sqrt(b) with correctly rounded square roots.  Deliberately not inlined: it is needed
+// once in a blue moon and must not be speculated into (or bloat) the hot loops.
+YSMR_HD_NOINLINE int sqrt_cmp(double a, double b)
+{
+    const double da = sqrt(a), db = sqrt(b);
+    return da < db ? -1 : (da > db ? 1 : 0);
+}
+
 YSMR_HD bool nearer(double s2_a, int qa, double s2_b, int qb)
 {
     const double eps = 8.8817841970012523e-16;   // 2^-50
     if (s2_b < s2_a * (1.0 - eps)) return true;
     if (s2_b > s2_a * (1.0 + eps)) return false;
-    const double da = sqrt(s2_a), db = sqrt(s2_b);
-    if (db != da) return db < da;
+    const int cmp = sqrt_cmp(s2_b, s2_a);
+    if (cmp != 0) return cmp < 0;
     return qb < qa;
 }
 
@@ -412,14 +480,15 @@ YSMR_HD int grid_nearest(const DetGrid &G, double ox, double oy, double *s2_out)
     const int kmax = (G.gw > G.gh ? G.gw : G.gh);
     for (int k = 0; k <= kmax; ++k) {
         const int x0 = cx - k, x1 = cx + k, y0 = cy - k, y1 = cy + k;
-        if (k == 0) grid_visit(G, cx, cy, ox, oy, best, arg);
-        else {
-            const int xa = x0 < 0 ? 0 : x0, xb = x1 >= G.gw ? G.gw - 1 : x1;
-            if (y0 >= 0) for (int x = xa; x <= xb; ++x) grid_visit(G, x, y0, ox, oy, best, arg);
-            if (y1 < G.gh) for (int x = xa; x <= xb; ++x) grid_visit(G, x, y1, ox, oy, best, arg);
-            const int ya = y0 + 1 < 0 ? 0 : y0 + 1, yb = y1 - 1 >= G.gh ? G.gh - 1 : y1 - 1;
-            if (x0 >= 0) for (int y = ya; y <= yb; ++y) grid_visit(G, x0, y, ox, oy, best, arg);
-            if (x1 < G.gw) for (int y = ya; y <= yb; ++y) grid_visit(G, x1, y, ox, oy, best, arg);
+        // the ring of cells at Chebyshev distance k, clipped to the grid (one visit site: rows y0 and y1 in full, the two
+        // end cells of the rows between)
+        const int xa = x0 < 0 ? 0 : x0, xb = x1 >= G.gw ? G.gw - 1 : x1;
+        const int ya = y0 < 0 ? 0 : y0, yb = y1 >= G.gh ? G.gh - 1 : y1;
+        for (int y = ya; y <= yb; ++y) {
+            const bool full = y == y0 || y == y1;
+            const int step = full || x1 == x0 ? 1 : x1 - x0;             // interior rows: only x0 and x1
+            for (int xx = full ? xa : x0; xx <= xb; xx += step)
+                if (xx >= 0) grid_visit(G, xx, y, ox, oy, best, arg);
         }
         // everything not visited yet lies outside the square of cells [x0, x1] x [y0, y1]
         const bool L = x0 <= 0, R = x1 >= G.gw - 1, T = y0 <= 0, B = y1 >= G.gh - 1;
