@@ -156,6 +156,14 @@ int ysmr_track_host(ysmr_ctx *ctx, const uint8_t *h_frames, int n_frames, int64_
 int ysmr_track_device(ysmr_ctx *ctx, const uint8_t *d_frames, int n_frames, int64_t frame_stride, int first_frame,
                       ysmr_row *d_rows, int64_t rows_capacity, int64_t *d_n_rows, void *stream);
 
+/* Row sink on the device (replaces helper_file.sort_list, /root/reference/ysmr/helper_file.py:1538-1574, for the rows
+ * of the hot loop): with ysmr_rows_archive(ctx, 1) every ysmr_track_host call also appends its rows to an archive in
+ * device memory (h_rows may then be NULL: nothing is copied back per call).  ysmr_rows_sorted groups the archive by
+ * (track_id, frame) -- the order of the final <video>_list.csv -- with a counting sort on the GPU and copies it to the
+ * host ONCE; with h_rows == NULL it only reports the count.  ysmr_rows_archive(ctx, 0) / ysmr_link_reset drop it. */
+int ysmr_rows_archive(ysmr_ctx *ctx, int enabled);
+int ysmr_rows_sorted(ysmr_ctx *ctx, ysmr_row *h_rows, int64_t rows_capacity, int64_t *n_rows);
+
 /* Development / measurement switches (not needed in production).  YSMR_OPT_FRONTEND_GEN: 4 (default) = the fused
  * bound-and-refine front-end kernel where it applies, 3 = always the three-kernel front-end of ABI 2 (bench.py's A/B
  * figure, and tests that hold one against the other). */

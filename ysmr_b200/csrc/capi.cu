@@ -81,6 +81,9 @@ struct ysmr_ctx {
     int32_t *pipe_count[2] = {nullptr, nullptr};
     float *pipe_blobs[2] = {nullptr, nullptr};
     ysmr_row *rows_dev = nullptr; int64_t rows_dev_cap = 0;
+    // device row archive (ysmr_rows_archive / ysmr_rows_sorted)
+    int archive_on = 0;
+    ysmr_row *arch = nullptr; int64_t arch_n = 0, arch_cap = 0;
     long long *n_rows_dev = nullptr;
     std::vector<void *> allocs;
     // optional per-kernel timing (ysmr_set_profiling): event pairs recorded around every launch on its own stream
@@ -341,6 +344,7 @@ int ysmr_destroy(ysmr_ctx *c)
         for (auto &pr : c->prof_events[k]) { cudaEventDestroy(pr.first); cudaEventDestroy(pr.second); }
     for (cudaEvent_t e : c->prof_free) cudaEventDestroy(e);
     if (c->rows_dev) cudaFree(c->rows_dev);
+    if (c->arch) cudaFree(c->arch);
     for (int i = 0; i < 2; ++i) {
         if (c->stage[i]) cudaFree(c->stage[i]);
         if (c->ev_copy[i]) cudaEventDestroy(c->ev_copy[i]);
@@ -657,10 +661,139 @@ int ysmr_track_device(ysmr_ctx *c, const uint8_t *d_frames, int n_frames, int64_
                         (cudaStream_t)stream);
 }
 
+// ---- row sink on the device: archive + counting sort by (track_id, frame) --------------------------------------------
+// Rows leave the linker frame-major, in insertion (= ascending id) order within a frame, and a track has a row in every
+// frame from its registration to its deregistration (track_eval.py:313-316 emits every live object).  So the position of a
+// row in the (TRACK_ID, POSITION_T) order of helper_file.sort_list is  offset[id] + (frame - first_frame[id])  with
+// offset = exclusive scan of the rows per id: one pass of atomics, one scan, one scatter -- no comparison sort.
+namespace {
+
+__global__ void rows_count_kernel(const ysmr_row *rows, int64_t n, int32_t *count, int32_t *first, int n_ids, int32_t *bad)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const int id = rows[i].track_id;
+        if (id < 0 || id >= n_ids) { atomicOr(bad, 1); continue; }
+        atomicAdd(&count[id], 1);
+        atomicMin(&first[id], rows[i].frame);
+    }
+}
+
+// exclusive scan of count[0 .. n) into offset (64-bit), one CTA
+__global__ void __launch_bounds__(1024) rows_scan_kernel(const int32_t *count, long long *offset, int n)
+{
+    __shared__ long long warp_tot[32];
+    __shared__ long long carry;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + t;
+        const long long v = i < n ? count[i] : 0;
+        long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += u; }
+        if (lane == 31) warp_tot[w] = inc;
+        __syncthreads();
+        if (w == 0) {
+            long long x = warp_tot[lane], y = x;
+            for (int o = 1; o < 32; o <<= 1) { const long long u = __shfl_up_sync(0xffffffffu, y, o); if (lane >= o) y += u; }
+            warp_tot[lane] = y - x;
+        }
+        __syncthreads();
+        const long long c0 = carry;
+        if (i < n) offset[i] = c0 + warp_tot[w] + inc - v;
+        __syncthreads();
+        if (t == 1023) carry = c0 + warp_tot[w] + inc;
+        __syncthreads();
+    }
+    if (t == 0) offset[n] = carry;
+}
+
+__global__ void rows_scatter_kernel(const ysmr_row *rows, int64_t n, const long long *offset, const int32_t *first, int n_ids,
+                                    ysmr_row *out, int32_t *bad)
+{
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const ysmr_row r = rows[i];
+        if (r.track_id < 0 || r.track_id >= n_ids) continue;
+        const long long dst = offset[r.track_id] + (long long)(r.frame - first[r.track_id]);
+        if (dst >= offset[r.track_id + 1]) { atomicOr(bad, 2); continue; }    // a gap in a track's frames: cannot happen
+        out[dst] = r;
+    }
+}
+
+}  // namespace
+
+int ysmr_rows_archive(ysmr_ctx *c, int enabled)
+{
+    if (!c) return YSMR_E_INVALID;
+    c->archive_on = enabled ? 1 : 0;
+    c->arch_n = 0;
+    if (!enabled && c->arch) { CU(c, cudaSetDevice(c->device)); CU(c, cudaDeviceSynchronize()); cudaFree(c->arch); c->arch = nullptr; c->arch_cap = 0; }
+    return YSMR_OK;
+}
+
+static int archive_append(ysmr_ctx *c, const ysmr_row *d_rows, int64_t n, cudaStream_t st)
+{
+    if (n <= 0) return YSMR_OK;
+    if (c->arch_n + n > c->arch_cap) {
+        int64_t cap = std::max<int64_t>(c->arch_cap * 2, std::max<int64_t>(c->arch_n + n, 1 << 20));
+        ysmr_row *bigger = nullptr;
+        CU(c, cudaMalloc((void **)&bigger, sizeof(ysmr_row) * (size_t)cap));
+        if (c->arch_n > 0) CU(c, cudaMemcpyAsync(bigger, c->arch, sizeof(ysmr_row) * (size_t)c->arch_n, cudaMemcpyDeviceToDevice, st));
+        CU(c, cudaStreamSynchronize(st));
+        if (c->arch) cudaFree(c->arch);
+        c->arch = bigger; c->arch_cap = cap;
+    }
+    CU(c, cudaMemcpyAsync(c->arch + c->arch_n, d_rows, sizeof(ysmr_row) * (size_t)n, cudaMemcpyDeviceToDevice, st));
+    c->arch_n += n;
+    return YSMR_OK;
+}
+
+int ysmr_rows_sorted(ysmr_ctx *c, ysmr_row *h_rows, int64_t rows_capacity, int64_t *n_rows)
+{
+    if (!c || !n_rows) return fail(c, YSMR_E_INVALID, "null argument");
+    if (!c->archive_on) return fail(c, YSMR_E_STATE, "ysmr_rows_archive has not been enabled");
+    *n_rows = c->arch_n;
+    if (!h_rows || c->arch_n == 0) return YSMR_OK;
+    if (rows_capacity < c->arch_n) return fail(c, YSMR_E_INVALID, "buffer too small");
+    CU(c, cudaSetDevice(c->device));
+    cudaStream_t st = c->s_link;
+    int32_t hdr[8];
+    CU(c, cudaStreamSynchronize(st));
+    CU(c, cudaMemcpy(hdr, c->ls.hdr, sizeof(hdr), cudaMemcpyDeviceToHost));
+    const int n_ids = hdr[1] > 0 ? hdr[1] : 1;
+    int32_t *count = nullptr, *first = nullptr, *bad = nullptr; long long *offset = nullptr; ysmr_row *sorted = nullptr;
+    cudaError_t e = cudaMalloc((void **)&count, sizeof(int32_t) * (size_t)(2 * n_ids + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&offset, sizeof(long long) * (size_t)(n_ids + 1));
+    if (e == cudaSuccess) e = cudaMalloc((void **)&sorted, sizeof(ysmr_row) * (size_t)c->arch_n);
+    int rc = YSMR_OK;
+    if (e != cudaSuccess) rc = fail(c, YSMR_E_CUDA, cudaGetErrorString(e));
+    else {
+        first = count + n_ids; bad = first + n_ids;
+        cudaMemsetAsync(count, 0, sizeof(int32_t) * (size_t)n_ids, st);
+        cudaMemsetAsync(first, 0x7f, sizeof(int32_t) * (size_t)n_ids, st);
+        cudaMemsetAsync(bad, 0, sizeof(int32_t), st);
+        const int grid = (int)std::min<int64_t>((c->arch_n + 255) / 256, 148 * 8);
+        rows_count_kernel<<<grid, 256, 0, st>>>(c->arch, c->arch_n, count, first, n_ids, bad);
+        rows_scan_kernel<<<1, 1024, 0, st>>>(count, offset, n_ids);
+        rows_scatter_kernel<<<grid, 256, 0, st>>>(c->arch, c->arch_n, offset, first, n_ids, sorted, bad);
+        c->launches += 3;
+        int32_t hbad = 0;
+        e = cudaMemcpyAsync(&hbad, bad, sizeof(hbad), cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(h_rows, sorted, sizeof(ysmr_row) * (size_t)c->arch_n, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) rc = fail(c, YSMR_E_CUDA, cudaGetErrorString(e));
+        else if (hbad) rc = fail(c, YSMR_E_STATE, "row archive is not frame-contiguous per track (rows from several videos?)");
+    }
+    if (count) cudaFree(count);
+    if (offset) cudaFree(offset);
+    if (sorted) cudaFree(sorted);
+    return rc;
+}
+
 int ysmr_track_host(ysmr_ctx *c, const uint8_t *h_frames, int n_frames, int64_t frame_stride, int first_frame,
                     ysmr_row *h_rows, int64_t rows_capacity, int64_t *n_rows)
 {
-    if (!c || !h_frames || !h_rows || !n_rows) return fail(c, YSMR_E_INVALID, "null argument");
+    if (!c || !h_frames || !n_rows || (!h_rows && !c->archive_on)) return fail(c, YSMR_E_INVALID, "null argument");
     if (n_frames < 0 || rows_capacity < 0) return fail(c, YSMR_E_INVALID, "negative size");
     int r = link_ready(c);
     if (r) return r;
@@ -679,7 +812,8 @@ int ysmr_track_host(ysmr_ctx *c, const uint8_t *h_frames, int n_frames, int64_t 
     CU(c, cudaMemcpyAsync(&n, c->n_rows_dev, sizeof(n), cudaMemcpyDeviceToHost, user));
     CU(c, cudaStreamSynchronize(user));
     if (n > rows_capacity) n = rows_capacity;
-    if (n > 0) CU(c, cudaMemcpy(h_rows, c->rows_dev, sizeof(ysmr_row) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (n > 0 && h_rows) CU(c, cudaMemcpy(h_rows, c->rows_dev, sizeof(ysmr_row) * (size_t)n, cudaMemcpyDeviceToHost));
+    if (c->archive_on) { r = archive_append(c, c->rows_dev, n, user); if (r) return r; CU(c, cudaStreamSynchronize(user)); }
     *n_rows = n;
     int32_t bits = 0, bad = -1;
     return ysmr_status(c, user, &bits, &bad);

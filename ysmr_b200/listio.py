@@ -48,6 +48,12 @@ def start_list(video_path, result_folder=None, rename_old_list=True):
     return old_list, csv_path
 
 
+def reset_list(csv_path):
+    """Back to the state right after start_list (header only)."""
+    with open(csv_path, 'w+', newline='') as fh:
+        fh.write(HEADER)
+
+
 def append_rows(csv_path, rows):
     """rows: structured array (api.ROW_DTYPE) in emission order.  One text line per row, formatted like
     '{0},{1},{2},{3},{4},{5},{6}'.format(int(id), int(frame), x, y, w, h, deg): x, y are float64 (repr), w/h/deg are the
