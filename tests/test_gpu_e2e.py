@@ -162,3 +162,24 @@ def test_properties_at_baseline_size():
         assert (d_pos['mask'][i].cpu().numpy() == r['mask']).all()
     for c in (ctx, inv, pos):
         c.close()
+
+
+def test_device_row_sink_equals_host_sort():
+    """the rows of a whole video grouped by (TRACK_ID, POSITION_T) on the device (counting sort over the row
+    archive, ysmr_rows_sorted) are byte-identical to a stable host sort of the rows the calls returned
+    (helper_file.sort_list, 1538-1574, sorts by the same keys)."""
+    from ysmr_b200.api import Context
+    cfg = SceneConfig(width=512, height=384, n_frames=90, n_cells=40, seed=5, margin=20.0)
+    grey = render_frames(make_scene(cfg))
+    ctx = Context(cfg.height, cfg.width, 1, 0, max_batch=16, max_blobs=512, max_tracks=1024)
+    ctx.archive_rows(True)
+    parts = [ctx.track_host(np.ascontiguousarray(grey[a:a + 13]), a, rows_capacity=13 * 1024).copy() for a in range(0, 90, 13)]
+    allr = np.concatenate(parts)
+    want = allr[np.lexsort((allr['frame'], allr['track_id']))]
+    got = ctx.rows_sorted()
+    assert len(got) == len(want) > 90 * 30 and got.tobytes() == want.tobytes()
+    # without the per-call copy the archive is all there is
+    ctx.reset(); ctx.archive_rows(True)
+    counts = [ctx.track_host(np.ascontiguousarray(grey[a:a + 13]), a, rows_capacity=13 * 1024, copy_rows=False) for a in range(0, 90, 13)]
+    assert sum(counts) == len(want) and ctx.rows_sorted().tobytes() == want.tobytes()
+    ctx.close()

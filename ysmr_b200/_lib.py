@@ -64,6 +64,8 @@ EXPORTS = {
     'ysmr_link_state_import': (C.c_int, [C.c_void_p, C.c_void_p, C.c_size_t]),
     'ysmr_link_live_tracks': (C.c_int, [C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     'ysmr_status': (C.c_int, [C.c_void_p, C.c_void_p, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    'ysmr_rows_archive': (C.c_int, [C.c_void_p, C.c_int]),
+    'ysmr_rows_sorted': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
     'ysmr_track_host': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64,
                                   C.POINTER(C.c_int64)]),
     'ysmr_track_device': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int64, C.c_int, C.c_void_p, C.c_int64,

@@ -191,17 +191,36 @@ class Context:
         k = int(n_rows.item())
         return rows_buf[:k * ROW_DTYPE.itemsize].cpu().numpy().view(ROW_DTYPE).copy()
 
-    def track_host(self, frames: np.ndarray, first_frame=0, rows_capacity=None, rows_out=None):
+    def archive_rows(self, enabled=True):
+        """Row sink on the device (SURVEY 8f.2): track_host calls also append their rows to an archive in device memory;
+        rows_sorted() returns the whole archive grouped by (track_id, frame) -- the order of the final csv -- sorted on
+        the GPU and copied to the host once."""
+        self._check(self.lib.ysmr_rows_archive(self._h, 1 if enabled else 0))
+        self._archive = bool(enabled)
+
+    def rows_sorted(self):
+        k = C.c_int64(0)
+        self._check(self.lib.ysmr_rows_sorted(self._h, None, 0, C.byref(k)))
+        out = np.empty(max(k.value, 1), ROW_DTYPE)
+        self._check(self.lib.ysmr_rows_sorted(self._h, out.ctypes.data_as(C.c_void_p), len(out), C.byref(k)))
+        return out[:k.value]
+
+    def track_host(self, frames: np.ndarray, first_frame=0, rows_capacity=None, rows_out=None, copy_rows=True):
         """detect + link over HOST frames (numpy uint8, ideally backed by pinned memory): H2D copies, kernels and the
-        D2H copy of the rows all happen inside the one C call."""
+        D2H copy of the rows all happen inside the one C call.  copy_rows=False (with archive_rows() on): the rows stay
+        in the device archive, the number of rows is returned instead."""
         shape = (self.height, self.width) if self.channels == 1 else (self.height, self.width, 3)
         if frames.dtype != np.uint8 or tuple(frames.shape[1:]) != shape or not frames.flags.c_contiguous:
             raise ValueError('frames must be C-contiguous uint8 (n, H, W[, 3])')
         n = int(frames.shape[0])
         cap = int(rows_capacity) if rows_capacity is not None else n * 256
+        k = C.c_int64(0)
+        if not copy_rows:
+            self._check(self.lib.ysmr_track_host(self._h, frames.ctypes.data_as(C.c_void_p), n, int(np.prod(shape)),
+                                                 int(first_frame), None, cap, C.byref(k)))
+            return int(k.value)
         if rows_out is None:
             rows_out = np.empty(max(cap, 1), ROW_DTYPE)
-        k = C.c_int64(0)
         self._check(self.lib.ysmr_track_host(self._h, frames.ctypes.data_as(C.c_void_p), n, int(np.prod(shape)),
                                              int(first_frame), rows_out.ctypes.data_as(C.c_void_p), cap, C.byref(k)))
         return rows_out[:k.value]

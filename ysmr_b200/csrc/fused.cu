@@ -172,16 +172,23 @@ __device__ __noinline__ void refine_px(const RefineCtx &rc, int idx)
 
 extern __shared__ __align__(16) unsigned char ysmr_fused_smem[];
 
-template <int C>
+// gp of fused_geometry for a tile width (a compile-time constant inside the kernel: the tile width is a template parameter,
+// so every division / multiplication by it or by the pitches derived from it folds)
+__host__ __device__ constexpr int fused_gp(int tw)
+{
+    int gp = tw + 24;
+    while (gp % 8 != 0 || (gp / 8) % 2 == 0) gp += 4;
+    return gp;
+}
+
+template <int C, int LTW>
 __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams p, FusedGeom g)
 {
     const int tid = threadIdx.x, lane = tid & 31;
-    // tile of this CTA
-    int bid = blockIdx.x;
-    const int tix = bid % g.tiles_x; bid /= g.tiles_x;
-    const int tiy = bid % g.tiles_y;
-    const int f = bid / g.tiles_y;
-    const int tw = g.tw, th = g.th, gp = g.gp, rp = g.rp;
+    // tile of this CTA: grid = (tiles_x, tiles_y, frames)
+    const int tix = blockIdx.x, tiy = blockIdx.y, f = blockIdx.z;
+    constexpr int tw = 1 << LTW, gp = fused_gp(tw);
+    const int th = g.th, rp = g.rp;
     const int tx0 = tix * tw, ty0 = tiy * th;
     const int W = p.w, H = p.h;
     const uint8_t *frame = p.frames + (int64_t)f * p.frame_stride;
@@ -190,10 +197,13 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     const uint32_t s_grey = s_base, s_rq = s_base, s_blur = s_base + g.off_blur, s_list = s_base + g.off_list;
     uint32_t *smask = reinterpret_cast<uint32_t *>(ysmr_fused_smem + g.off_mask);
     FusedMisc *misc = reinterpret_cast<FusedMisc *>(ysmr_fused_smem + g.off_misc);
-    const int lmw = g.ltw - 5, mw = 1 << lmw;                     // mask words per tile row
+    constexpr int lmw = LTW - 5, mw = 1 << lmw;                   // mask words per tile row
     const int n_mask = th * mw;
 
-    for (int i = tid; i < 2 * n_mask; i += FT_THREADS) smask[i] = 0u;
+    {   // (n_mask is a multiple of 4 words: th % 4 == 0; the mask tiles are 16-byte aligned)
+        uint4 *sm4 = reinterpret_cast<uint4 *>(smask);
+        for (int i = tid; i < n_mask / 2; i += FT_THREADS) sm4[i] = make_uint4(0u, 0u, 0u, 0u);
+    }
     if (tid == 0) { misc->tmin = 0xFFFFu; misc->tmax = 0u; misc->count = 0u; }
 
     // ---- 1a: grey tile.  Row r <-> virtual image row ty0 - 6 + r, byte c <-> virtual column tx0 - 12 + c.  The blur reads
@@ -227,27 +237,53 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
                 asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(so), "r"(__byte_perm(va, va, sela)), "r"(__byte_perm(vb, vb, selb)));
                 so += rstep * gp;
             };
-            // software pipeline: the loads of the next three rows are issued before the current three are converted
             typedef uint32_t Raw[2][C == 3 ? 3 : 1];
-            Raw x0, x1, x2, y0, y1, y2;
-            int r = r0;
-            const int step3 = 3 * rstep;
-            auto load3 = [&](int rr, Raw &a, Raw &b, Raw &c) {
-                if (rr < n_rows) load(rr, a);
-                if (rr + rstep < n_rows) load(rr + rstep, b);
-                if (rr + 2 * rstep < n_rows) load(rr + 2 * rstep, c);
-            };
-            auto store3 = [&](int rr, const Raw &a, const Raw &b, const Raw &c) {
-                if (rr < n_rows) store(a);
-                if (rr + rstep < n_rows) store(b);
-                if (rr + 2 * rstep < n_rows) store(c);
-            };
-            load3(r, x0, x1, x2);
-            for (; r < n_rows; r += 2 * step3) {
-                load3(r + step3, y0, y1, y2);
-                store3(r, x0, x1, x2);
-                load3(r + 2 * step3, x0, x1, x2);
-                store3(r + step3, y0, y1, y2);
+            if (y_inside) {
+                // interior tile (the common case): every row is an image row, the row pointer just advances, and rows
+                // stream through a three-deep register pipeline (two rows of loads in flight while one is converted)
+                const int gy0 = ty0 - 6 + r0;
+                const uint8_t *pa = frame + gy0 * rowstride + offa;
+                const int64_t dab = offb - offa, adv = rstep * rowstride;
+                auto ld = [&](Raw &raw) {
+                    const uint32_t *qa = reinterpret_cast<const uint32_t *>(pa), *qb = reinterpret_cast<const uint32_t *>(pa + dab);
+                    raw[0][0] = __ldg(qa); raw[1][0] = __ldg(qb);
+                    if (C == 3) { raw[0][1] = __ldg(qa + 1); raw[0][2] = __ldg(qa + 2); raw[1][1] = __ldg(qb + 1); raw[1][2] = __ldg(qb + 2); }
+                    pa += adv;
+                };
+                const int cnt = (n_rows - r0 + rstep - 1) / rstep;       // rows of this thread (>= 3: th >= 16)
+                Raw a, b, c;
+                ld(a); ld(b);
+                int k = 0;
+                for (; k + 3 <= cnt - 2; k += 3) {
+                    ld(c); store(a);
+                    ld(a); store(b);
+                    ld(b); store(c);
+                }
+                // drain: rows k .. cnt-1 (a, b hold rows k, k+1)
+                if (k + 2 < cnt) { ld(c); store(a); if (k + 3 < cnt) { ld(a); store(b); store(c); store(a); } else { store(b); store(c); } }
+                else { store(a); store(b); }
+            } else {
+                // software pipeline: the loads of the next three rows are issued before the current three are converted
+                Raw x0, x1, x2, y0, y1, y2;
+                int r = r0;
+                const int step3 = 3 * rstep;
+                auto load3 = [&](int rr, Raw &a, Raw &b, Raw &c) {
+                    if (rr < n_rows) load(rr, a);
+                    if (rr + rstep < n_rows) load(rr + rstep, b);
+                    if (rr + 2 * rstep < n_rows) load(rr + 2 * rstep, c);
+                };
+                auto store3 = [&](int rr, const Raw &a, const Raw &b, const Raw &c) {
+                    if (rr < n_rows) store(a);
+                    if (rr + rstep < n_rows) store(b);
+                    if (rr + 2 * rstep < n_rows) store(c);
+                };
+                load3(r, x0, x1, x2);
+                for (; r < n_rows; r += 2 * step3) {
+                    load3(r + step3, y0, y1, y2);
+                    store3(r, x0, x1, x2);
+                    load3(r + 2 * step3, x0, x1, x2);
+                    store3(r + step3, y0, y1, y2);
+                }
             }
         }
     }
@@ -297,7 +333,7 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     if (p.dbg_grey || p.dbg_blurred) {
         const int64_t plane = (int64_t)H * W;
         for (int i = tid; i < tw * th; i += FT_THREADS) {
-            const int yy = i >> g.ltw, xx = i & (tw - 1);
+            const int yy = i >> LTW, xx = i & (tw - 1);
             const int x = tx0 + xx, y = ty0 + yy;
             if (x < W && y < H) {
                 if (p.dbg_grey) p.dbg_grey[f * plane + (int64_t)y * W + x] = ysmr_fused_smem[(yy + 6) * gp + 12 + xx];
@@ -357,14 +393,14 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     const int acc_row = inv ? BH_SUM * tmax : -BH_SUM * tmin;     // start of the row chain: sum h (p - base_p) >= 0
     const int ka = inv ? (int)KAn : (int)KA, kb = inv ? (int)KBn : (int)KB, kc = inv ? (int)KCn : (int)KC;
     const int ka2 = inv ? (int)KA2n : (int)KA2, kb2 = inv ? (int)KB2n : (int)KB2, kc2 = inv ? (int)KC2n : (int)KC2;
-    const int nq2 = tw >> 2;                                      // row-pass bytes of pixel pair X live in column
+    constexpr int nq2 = tw >> 2;                                     // row-pass bytes of pixel pair X live in column
                                                                   // X/2 (X even) or nq2 + X/2 (X odd) of the rq array
 
     // ---- 2a: row pass.  Task (q, G): pixels 8q .. 8q+7 of the four blurred rows ry = 4G .. 4G+3 (tile row ry + 1, image row
     // ty0 - 4 + ry) -> four pair results X = 4q .. 4q+3 per row, shifted to a byte, the four rows of a pair as one word of the
     // transposed array rq[col(X)][ry].  Lanes run along q: consecutive LDS.64.
     {
-        const int lq = g.ltw - 3, nq = 1 << lq, nG = (th + 8) >> 2;
+        constexpr int lq = LTW - 3, nq = 1 << lq; const int nG = (th + 8) >> 2;
         for (int t = tid; t < nq * nG; t += FT_THREADS) {
             const int q = t & (nq - 1), G = t >> lq;
             uint32_t a = s_blur + (4 * G + 1) * gp + 8 * q + 8;                   // relative words 2q-1 .. 2q+2
@@ -393,7 +429,7 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     __syncthreads();
 
     RefineCtx rc;
-    rc.s_blur = s_blur; rc.gp = gp; rc.tw = tw; rc.ltw = g.ltw; rc.mw = mw; rc.n_mask = n_mask; rc.tx0 = tx0;
+    rc.s_blur = s_blur; rc.gp = gp; rc.tw = tw; rc.ltw = LTW; rc.mw = mw; rc.n_mask = n_mask; rc.tx0 = tx0;
     rc.row_tail_from = p.row_tail_from; rc.col_tail_from = p.col_tail_from; rc.t_mask = p.t_mask; rc.t_marker = p.t_marker;
     rc.inv = inv; rc.two = p.marker_bits != nullptr; rc.smask = smask;
     const int list_cap = g.list_cap;
@@ -409,7 +445,7 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
     // range <= 127 (any tile that is not saturated): byte-parallel test  q + A >= 128  <=>  q > T  with A = clamp(127 - T, 0, 128),
     // and A comes straight out of the dot-product chain run with negated weights.
     {
-        const int lj = g.ltw - 2, nj = 1 << lj, nm = th >> 2;
+        constexpr int lj = LTW - 2, nj = 1 << lj; const int nm = th >> 2;
         const int ts = 16 - sh;
         const int c0 = (g.t_q * 65536 + 31457) >> sh;             // arithmetic shift: floor, i.e. towards "candidate"
         const bool swar = range <= 127;
@@ -544,18 +580,25 @@ bool fused_frontend_supported(const FrontParams &p)
 // per device (the attribute is per device / context): called from ysmr_create
 cudaError_t fused_frontend_init()
 {
-    cudaError_t e = cudaFuncSetAttribute(fused_front_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(fused_front_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(fused_front_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_front_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_front_kernel<3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_front_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    return e;
 }
 
 cudaError_t launch_fused_frontend(const FrontParams &p, cudaStream_t st)
 {
     const FusedGeom g = fused_geometry(p);
-    const int64_t ctas = (int64_t)g.tiles_x * g.tiles_y * p.n_frames;
-    if (ctas > 0x7fffffff || g.smem_bytes > 100 * 1024) return cudaErrorInvalidConfiguration;
-    if (p.channels == 3) fused_front_kernel<3><<<(unsigned)ctas, FT_THREADS, g.smem_bytes, st>>>(p, g);
-    else fused_front_kernel<1><<<(unsigned)ctas, FT_THREADS, g.smem_bytes, st>>>(p, g);
+    if (g.tiles_y > 65535 || p.n_frames > 65535 || g.smem_bytes > 100 * 1024 || g.gp != fused_gp(g.tw)) return cudaErrorInvalidConfiguration;
+    const dim3 grid((unsigned)g.tiles_x, (unsigned)g.tiles_y, (unsigned)p.n_frames);
+    if (p.channels == 3) {
+        if (g.ltw == 8) fused_front_kernel<3, 8><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
+        else fused_front_kernel<3, 7><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
+    } else {
+        if (g.ltw == 8) fused_front_kernel<1, 8><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
+        else fused_front_kernel<1, 7><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
+    }
     return cudaGetLastError();
 }
 

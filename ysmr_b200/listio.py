@@ -92,8 +92,9 @@ def sort_list(csv_path, save_file=True):
     return df
 
 
-def write_sorted(csv_path, rows, save_file=True):
-    """Row sink with a single write: the rows of the whole video (api.ROW_DTYPE, emission order) are
+def write_sorted(csv_path, rows, save_file=True, presorted=False):
+    """Row sink with a single write: the rows of the whole video (api.ROW_DTYPE; emission order, or -- with
+    presorted=True -- already grouped by (track_id, frame) on the device, Context.rows_sorted, so that no host sort runs) are
     formatted as the hot loop would have appended them, parsed back IN MEMORY by the same pandas call as
     helper_file.get_data, sorted by (TRACK_ID, POSITION_T) and written once.  The parse cannot be skipped: pandas' default
     float parser is not round-trip exact (10.494321823120117 comes back as 10.494321823120115), and that last-digit
@@ -101,8 +102,9 @@ def write_sorted(csv_path, rows, save_file=True):
     import io
     import pandas as pd
     df = pd.read_csv(io.StringIO(HEADER + format_rows(rows)), sep=',', header=0, usecols=list(DTYPES.keys()), dtype=DTYPES)
-    df.sort_values(by=['TRACK_ID', 'POSITION_T'], inplace=True, na_position='first')
-    df.reset_index(drop=True, inplace=True)
+    if not presorted:
+        df.sort_values(by=['TRACK_ID', 'POSITION_T'], inplace=True, na_position='first')
+        df.reset_index(drop=True, inplace=True)
     if save_file:
         with open(csv_path, 'w+', newline='\n') as fh:
             df.to_csv(fh, index=False, encoding='utf-8')

@@ -133,7 +133,11 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
             # Ingest: reader threads decode the coming chunks into pinned buffers while the GPU works on the
             # current one (cv2.VideoCapture.read and the ctypes call both release the GIL)
             reader = ingest.ChunkReader(video_path, frame_count, frame_height, frame_width, channels, chunk_frames, n_readers)
-            rows_out = np.empty(min(chunk_frames * max_tracks, 1 << 22), ROW_DTYPE)
+            rows_cap = min(chunk_frames * max_tracks, 1 << 22)
+            once = row_sink == 'once'
+            rows_out = None if once else np.empty(rows_cap, ROW_DTYPE)
+            if once:                       # rows stay on the device and come back sorted, once
+                ctx.archive_rows(True)
             pending, n_pending = [], 0     # rows not yet written (flushed every 'list save length interval' rows)
             curr, last_live, read_error = 0, 0, False
             for buf, idx, n, last in reader:
@@ -145,13 +149,16 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
                         logger.critical('Error during cap.read() with file {}'.format(video_path))
                         read_error = settings['stop evaluation on error']
                 if n:
-                    rows = ctx.track_host(buf, curr, rows_capacity=len(rows_out), rows_out=rows_out)
-                    pending.append(rows.copy()); n_pending += len(rows)
+                    if once:
+                        ctx.track_host(buf, curr, rows_capacity=rows_cap, copy_rows=False)
+                    else:
+                        rows = ctx.track_host(buf, curr, rows_capacity=rows_cap, rows_out=rows_out)
+                        pending.append(rows.copy()); n_pending += len(rows)
                     curr += n
                     last_live = ctx.live_tracks()[0]
                     # row_sink 'append' (default): the reference's life cycle, text appended every 'list save length
-                    # interval' rows and sorted through a read-back at the end; 'once': rows stay in memory and the sorted
-                    # file is written a single time (listio.write_sorted) -- same bytes
+                    # interval' rows and sorted through a read-back at the end; 'once': rows stay on the device, are
+                    # grouped by (TRACK_ID, POSITION_T) there and written a single time -- same bytes
                     if row_sink == 'append' and n_pending >= settings['list save length interval']:
                         listio.append_rows(list_name, np.concatenate(pending))
                         pending, n_pending = [], 0
@@ -159,7 +166,7 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
             if pending and row_sink == 'append':
                 listio.append_rows(list_name, np.concatenate(pending))
                 pending = []
-            return pending, curr, last_live, read_error
+            return (ctx.rows_sorted() if once else None), curr, last_live, read_error
         finally:
             if reader is not None:
                 reader.close()
@@ -190,7 +197,7 @@ def track_bacteria(video_path, settings=None, result_folder=None, *, device=0, c
     if row_sink == 'append':
         df_for_eval = listio.sort_list(list_name, save_file=not settings['delete .csv file after analysis'])
     else:
-        all_rows = np.concatenate(pending) if pending else np.empty(0, ROW_DTYPE)
-        df_for_eval = listio.write_sorted(list_name, all_rows, save_file=not settings['delete .csv file after analysis'])
+        df_for_eval = listio.write_sorted(list_name, pending, save_file=not settings['delete .csv file after analysis'],
+                                          presorted=True)
     logger.info('frames: {:>6} of {:>6}, csv: {}'.format(curr_frame_count, frame_count, list_name))
     return df_for_eval, fps_of_file, frame_height, frame_width, list_name
