@@ -1,14 +1,18 @@
 import numpy as np, torch, sys
 sys.path.insert(0,'.')
 from ysmr_b200.api import Context
-from ysmr_b200.synth import SceneConfig, make_scene, render_frames_torch
+from ysmr_b200.synth import CONFIGS, SceneConfig, make_scene, render_frames_torch
+import dataclasses
 import os
 F=int(os.environ.get('LINKPROF_FRAMES','1024'))
 PLAIN=bool(os.environ.get('LINKPROF_PLAIN'))
-scene=make_scene(SceneConfig(n_frames=F,n_cells=50,seed=0))
-fr=torch.empty((F,922,1228),dtype=torch.uint8,device='cuda')
-for a in range(0,F,128): render_frames_torch(scene,a,a+128,'cuda',1,out=fr[a:a+128])
-ctx=Context(922,1228,1,0,max_batch=256,max_blobs=512,max_tracks=1024)
+CFG=os.environ.get('LINKPROF_CFG','cfg2')
+cfg=dataclasses.replace(CONFIGS[CFG],n_frames=F)
+scene=make_scene(cfg)
+H,W=cfg.height,cfg.width
+fr=torch.empty((F,H,W),dtype=torch.uint8,device='cuda')
+for a in range(0,F,64): render_frames_torch(scene,a,min(F,a+64),'cuda',1,out=fr[a:min(F,a+64)])
+ctx=Context(H,W,1,0,max_batch=256,max_blobs=4096 if CFG=='cfg3' else 512,max_tracks=8192,white_on_dark=CFG!='cfg4')
 cs=[];bs=[]
 for a in range(0,F,256):
     c,b=ctx.detect(fr[a:a+256],a); cs.append(c); bs.append(b)
@@ -17,7 +21,7 @@ for rep in range(2):
     ctx.reset(); ctx.set_profiling(True, link_phases=not PLAIN)
     torch.cuda.synchronize()
     e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
-    e0.record(); rows=ctx.link(counts,blobs,0,F*100); e1.record(); torch.cuda.synchronize()
+    e0.record(); rows=ctx.link(counts,blobs,0,F*(3000 if CFG=='cfg3' else 400)); e1.record(); torch.cuda.synchronize()
     pc=ctx.link_phase_cycles()
     print('link ms', e0.elapsed_time(e1), 'rows', len(rows), 'frames', pc[12])
     names=['loop top + staging','candidate/scan/claim','barrier 2','conflict+outcome','barrier 4 (vote)','events','gsff','row + loop end']

@@ -77,6 +77,9 @@ def ysmr(paths=None, settings=None, result_folder=None, multiprocess=False):
     if install():
         import ysmr.main as ref_main
         # process-per-video (main.py:281-288) would need the rebinding in every child; videos are GPU-bound anyway
+        if multiprocess:
+            logging.getLogger('ysmr').getChild(__name__).warning(
+                'multiprocess=True is ignored by the B200 path: videos are processed one after the other on the GPU.')
         return ref_main.ysmr(paths=paths, settings=settings, result_folder=result_folder, multiprocess=False)
     settings = get_configs(settings)
     if settings is None:
@@ -86,6 +89,9 @@ def ysmr(paths=None, settings=None, result_folder=None, multiprocess=False):
         paths = [paths]
     if not paths:
         return None
+    if multiprocess:
+        logging.getLogger('ysmr').getChild(__name__).warning(
+            'multiprocess=True is ignored by the B200 path: videos are processed one after the other on the GPU.')
     finished = []
     for p in [os.path.expanduser(q) for q in paths]:
         finished.append((p, analyse(p, settings=settings, result_folder=result_folder)))
