@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define YSMR_ABI_VERSION 3
+#define YSMR_ABI_VERSION 4
 
 enum {
     YSMR_OK = 0,
@@ -163,6 +163,50 @@ int ysmr_track_device(ysmr_ctx *ctx, const uint8_t *d_frames, int n_frames, int6
  * host ONCE; with h_rows == NULL it only reports the count.  ysmr_rows_archive(ctx, 0) / ysmr_link_reset drop it. */
 int ysmr_rows_archive(ysmr_ctx *ctx, int enabled);
 int ysmr_rows_sorted(ysmr_ctx *ctx, ysmr_row *h_rows, int64_t rows_capacity, int64_t *n_rows);
+
+/* ---- Track selection: the data-parallel body of select_tracks() / find_good_tracks(),
+ * /root/reference/ysmr/track_eval.py:408-843, on the rows of <video>_list.csv.  Values are the reference's settings AFTER
+ * get_configs() (helper_file.py:777-786: percentages already divided by 100, 'maximal empty frames in %' / 100 + 1). */
+typedef struct ysmr_select_params {
+    double  area_lo, area_hi;       /* 'extreme area outliers lower / upper end in px*px' (track_eval.py:624-630)       */
+    double  area_factor;            /* 'exclude measurement when above x times average area', 0 = off (:632-637)         */
+    double  q_area;                 /* 'percent quantiles excluded area' (fraction), <= 0 = off (:703-712)               */
+    double  stop_outliers_above;    /* 'stop excluding motility outliers if total count above percent' (fraction, :728) */
+    double  max_empty;              /* 'maximal empty frames in %' (:471)                                                 */
+    double  ratio_min, ratio_max;   /* 'average width/height ratio min. / max.' (:478-480)                                */
+    double  edge;                   /* 'percent of screen edges to exclude' (fraction, :483-494)                          */
+    int32_t min_len_frames;         /* int(round(fps) * 'minimal length in seconds') (:586)                               */
+    int32_t limit_frames;           /* int(round(fps) * 'limit track length to x seconds'), 0 = off (:587, 781)           */
+    int32_t limit_exactly;          /* 'limit track length exactly' (:785-790)                                            */
+    int32_t omit_motility_outliers; /* 'try to omit motility outliers' (:713)                                             */
+    int32_t max_holes;              /* 'maximal consecutive holes' (:462)                                                 */
+    int32_t max_recursion;          /* 'maximal recursion depth' (:507-509), 0 .. 4000                                    */
+    int32_t frame_h, frame_w;
+} ysmr_select_params;
+
+enum {                              /* indices of the info array of ysmr_select_tracks */
+    YSMR_SI_STATUS = 0,             /* YSMR_SEL_* */
+    YSMR_SI_ROWS_BEFORE = 1, YSMR_SI_ROWS_AFTER = 2, YSMR_SI_TRACKS_BEFORE = 3, YSMR_SI_TRACKS_AFTER = 4,   /* log line :686-691 */
+    YSMR_SI_Q1_AREA = 5, YSMR_SI_Q3_AREA = 6, YSMR_SI_Q1_DIST = 7, YSMR_SI_Q3_DIST = 8, YSMR_SI_FENCE = 9,
+    YSMR_SI_OUTLIERS = 10, YSMR_SI_OUTLIERS_OFF = 11, YSMR_SI_GOOD_TRACKS = 12, YSMR_SI_LAUNCHES = 13,
+    YSMR_SELECT_INFO = 16
+};
+enum {
+    YSMR_SEL_OK = 0,
+    YSMR_SEL_TOO_SHORT_BEFORE = 1,  /* fewer rows than the minimal length before the clean-up: the reference returns None (:599-606) */
+    YSMR_SEL_TOO_SHORT_AFTER = 2,   /* ... after the clean-up (:676-684) */
+    YSMR_SEL_NO_TRACKS = 3          /* no track passed (:816-819) */
+};
+
+/* n_rows rows grouped by (TRACK_ID, POSITION_T) in HOST memory, columns as the reference's data frame holds them
+ * (uint32, uint32, float64 x 4).  Outputs (HOST): h_good[n_rows] = 1 for the rows of the selected fragments
+ * (df['good_track'], :822-828); h_clean_index[n_rows] = the row's index after the initial clean-up (the 'index' column
+ * reset_index leaves in the returned frame, :834) or -1 if the clean-up dropped it; kick_reasons[9] (:749, 796-812);
+ * info[YSMR_SELECT_INFO].  Synchronous; runs on `device`. */
+int ysmr_select_tracks(int device, int64_t n_rows, const uint32_t *h_track_id, const uint32_t *h_t, const double *h_x,
+                       const double *h_y, const double *h_w, const double *h_h, const ysmr_select_params *params,
+                       uint8_t *h_good, int32_t *h_clean_index, int64_t *kick_reasons, double *info);
+const char *ysmr_select_last_error(void);
 
 /* Development / measurement switches (not needed in production).  YSMR_OPT_FRONTEND_GEN: 4 (default) = the fused
  * bound-and-refine front-end kernel where it applies, 3 = always the three-kernel front-end of ABI 2 (bench.py's A/B

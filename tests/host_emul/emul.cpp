@@ -243,3 +243,34 @@ void emul_set_order(int32_t *keys, int n)
 }
 
 }  // extern "C"
+
+#include "../../ysmr_b200/csrc/select.cuh"
+
+extern "C" {
+
+// ndarray.sum() / n as csrc/select.cuh restates it (checked against numpy / pandas in tests/test_select_host.py)
+double emul_np_mean(const double *a, int64_t n) { return np_mean(a, n); }
+double emul_np_sum(const double *a, int64_t n) { return np_pairwise_sum(a, n); }
+
+// find_good_tracks for every track of a cleaned-up frame (single lane).  cfg: the SelectCfg fields in declaration order
+// as doubles.  Outputs per track: good_start, good_stop (-1 = none), kick reason.
+void emul_select_tracks(const int32_t *track_start, int n_tracks, int n_rows, const uint32_t *t, const double *x, const double *y,
+                        const double *area, const double *ratio, const int8_t *outlier, const double *cfg, int32_t *good_start,
+                        int32_t *good_stop, int32_t *kick)
+{
+    SelectCols c{t, x, y, area, ratio, outlier};
+    SelectCfg g{};
+    g.min_len = (int)cfg[0]; g.max_holes = (int)cfg[1]; g.max_recursion = (int)cfg[2]; g.max_empty = cfg[3]; g.lower = cfg[4];
+    g.upper = cfg[5]; g.ratio_min = cfg[6]; g.ratio_max = cfg[7]; g.edge = cfg[8]; g.frame_h = (int)cfg[9]; g.frame_w = (int)cfg[10];
+    g.limit_frames = (int)cfg[11]; g.limit_exactly = (int)cfg[12];
+    std::vector<SelectSeg> stack(g.max_recursion + 2);
+    const OneLane one;
+    for (int k = 0; k < n_tracks; ++k) {
+        const int lo = track_start[k], hi = (k + 1 < n_tracks ? track_start[k + 1] : n_rows) - 1;
+        int gs = -1, ge = -1;
+        kick[k] = select_track(one, c, g, lo, hi, stack.data(), (int)stack.size(), &gs, &ge);
+        good_start[k] = gs; good_stop[k] = ge;
+    }
+}
+
+}  // extern "C"

@@ -45,6 +45,21 @@ class DebugOut(C.Structure):
                 ('d_scalar_thr', C.c_void_p)]
 
 
+class SelectParams(C.Structure):
+    """struct ysmr_select_params"""
+    _fields_ = [('area_lo', C.c_double), ('area_hi', C.c_double), ('area_factor', C.c_double), ('q_area', C.c_double),
+                ('stop_outliers_above', C.c_double), ('max_empty', C.c_double), ('ratio_min', C.c_double),
+                ('ratio_max', C.c_double), ('edge', C.c_double), ('min_len_frames', C.c_int32), ('limit_frames', C.c_int32),
+                ('limit_exactly', C.c_int32), ('omit_motility_outliers', C.c_int32), ('max_holes', C.c_int32),
+                ('max_recursion', C.c_int32), ('frame_h', C.c_int32), ('frame_w', C.c_int32)]
+
+
+# indices of the info array of ysmr_select_tracks (include/ysmr_b200.h)
+SI_STATUS, SI_ROWS_BEFORE, SI_ROWS_AFTER, SI_TRACKS_BEFORE, SI_TRACKS_AFTER = 0, 1, 2, 3, 4
+SI_Q1_AREA, SI_Q3_AREA, SI_Q1_DIST, SI_Q3_DIST, SI_FENCE, SI_OUTLIERS, SI_OUTLIERS_OFF, SI_GOOD_TRACKS, SI_LAUNCHES = range(5, 14)
+SELECT_INFO = 16
+SEL_OK, SEL_TOO_SHORT_BEFORE, SEL_TOO_SHORT_AFTER, SEL_NO_TRACKS = 0, 1, 2, 3
+
 EXPORTS = {
     # name: (restype, argtypes)
     'ysmr_abi_version': (C.c_int, []),
@@ -75,6 +90,9 @@ EXPORTS = {
     'ysmr_set_profiling': (C.c_int, [C.c_void_p, C.c_int]),
     'ysmr_get_profile': (C.c_int, [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_int64)]),
     'ysmr_link_phase_cycles': (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
+    'ysmr_select_tracks': (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.POINTER(SelectParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'ysmr_select_last_error': (C.c_char_p, []),
 }
 
 _lib = None
