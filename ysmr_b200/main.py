@@ -1,11 +1,12 @@
 """``ysmr()`` / ``analyse()`` with the reference's signatures (ysmr/main.py:32-172, 175-331), routing videos to the B200
 ``track_bacteria``.
 
-The stages after tracking (select_tracks, evaluate_tracks, annotate_video -- SURVEY section 2, rows 7-9) are out of scope
-of this repository and are NOT re-implemented: when the reference package ``ysmr`` is importable, :func:`install`
-rebinds its ``track_bacteria`` to ours and these wrappers simply call the reference's own drivers, so every later stage,
-log line and file of the reference is produced by the reference's code on our ``_list.csv``.  Without the reference
-package the wrappers run the tracking stage only and keep the return conventions (DataFrame / True / None; list of
+Of the stages after tracking, ``select_tracks`` runs on the GPU as well (``ysmr_b200/select.py``);
+``evaluate_tracks`` and ``annotate_video`` are out of scope of this repository and are NOT
+re-implemented: when the reference package ``ysmr`` is importable, :func:`install` rebinds its ``track_bacteria`` and
+``select_tracks`` to ours and these wrappers simply call the reference's own drivers, so every later stage, log line and
+file of the reference is produced by the reference's code on our ``_list.csv`` / selected rows.  Without the reference
+package the wrappers run tracking and selection and keep the return conventions (DataFrame / True / None; list of
 ``(path, result)``).
 """
 from __future__ import annotations
@@ -13,6 +14,7 @@ from __future__ import annotations
 import logging
 import os
 
+from .select import select_tracks
 from .settings import get_configs
 from .track_eval import track_bacteria
 
@@ -22,8 +24,8 @@ _saved = {}
 
 
 def install():
-    """Make the reference use the GPU path: rebinds ``ysmr.main.track_bacteria`` (imported by name at main.py:27) and
-    ``ysmr.track_eval.track_bacteria``.  Returns True when the reference package was found."""
+    """Make the reference use the GPU path: rebinds ``track_bacteria`` and ``select_tracks`` in ``ysmr.main`` (imported by
+    name at main.py:27) and in ``ysmr.track_eval``.  Returns True when the reference package was found."""
     try:
         import ysmr.main as ref_main
         import ysmr.track_eval as ref_te
@@ -32,8 +34,12 @@ def install():
     if 'main' not in _saved:
         _saved['main'] = ref_main.track_bacteria
         _saved['te'] = ref_te.track_bacteria
+        _saved['main_sel'] = ref_main.select_tracks
+        _saved['te_sel'] = ref_te.select_tracks
     ref_main.track_bacteria = track_bacteria
     ref_te.track_bacteria = track_bacteria
+    ref_main.select_tracks = select_tracks
+    ref_te.select_tracks = select_tracks
     return True
 
 
@@ -43,6 +49,8 @@ def uninstall():
         import ysmr.track_eval as ref_te
         ref_main.track_bacteria = _saved.pop('main')
         ref_te.track_bacteria = _saved.pop('te')
+        ref_main.select_tracks = _saved.pop('main_sel')
+        ref_te.select_tracks = _saved.pop('te_sel')
 
 
 def analyse(path, settings=None, result_folder=None, return_df=False, **kwargs):
@@ -58,19 +66,28 @@ def analyse(path, settings=None, result_folder=None, return_df=False, **kwargs):
     if any(ext in path for ext in ('_analysed.csv', '_statistics.csv', '_annotated_output.')):
         logger.warning('File already evaluated. File: {}'.format(path))
         return None
-    if '.csv' in path:
-        logger.warning('Only the tracking stage is available without the reference package; got a .csv: {}'.format(path))
-        return None
-    res = track_bacteria(video_path=path, settings=settings, result_folder=result_folder)
-    if res is None:
-        logger.warning('Error during video analysis of file {}.'.format(path))
-        return None
-    if settings.get('delete .csv file after analysis'):
+    # main.py:86-127: a video is tracked first, a *_list.csv goes straight to the selection, a *_selected_data.csv is done
+    df, csv_file, meta = None, None, dict(kwargs)
+    if '.csv' not in path:
+        res = track_bacteria(video_path=path, settings=settings, result_folder=result_folder)
+        if res is None:
+            logger.warning('Error during video analysis of file {}.'.format(path))
+            return None
+        df, fps, height, width, csv_file = res
+        meta.update(fps=fps, frame_height=height, frame_width=width)
+        path = csv_file
+    if 'selected_data.csv' not in path:
+        df = select_tracks(path_to_file=path, df=df, results_directory=result_folder, settings=settings, **meta)
+        if df is None:
+            logger.warning('Error during video analysis of file {}.'.format(path))
+    if settings.get('delete .csv file after analysis') and csv_file:
         try:
-            os.remove(res[4])
+            os.remove(csv_file)
         except OSError:
             pass
-    return res[0] if return_df else True
+    if df is None:
+        return None
+    return df if return_df else True
 
 
 def ysmr(paths=None, settings=None, result_folder=None, multiprocess=False):
