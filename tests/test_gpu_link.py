@@ -97,3 +97,27 @@ def test_track_and_row_overflow_are_loud():
     with pytest.raises(YsmrError):
         ctx.link(torch.from_numpy(counts).cuda(), torch.from_numpy(blobs).cuda(), 0, 7)
     ctx.close()
+
+
+@pytest.mark.parametrize('mode', ['general,cta', 'general,grid', 'grid'])
+def test_general_kernels_single_cta_and_cooperative_grid(monkeypatch, mode):
+    """The general path (any number of tracks / detections) as one CTA and as a cooperative grid, with and without the lane
+    fast path in front of it: same rows as the reference on the golden sequences and on a fresh dense one."""
+    from oracle.make_golden import random_detection_sequence
+    from oracle.tracker_port import LinkerPort
+    monkeypatch.setenv('YSMR_LINK', mode)
+    for path in sorted(glob.glob(os.path.join(GOLDEN, 'link_*_gsff.npz'))):
+        g = np.load(path)
+        got, _ = _run(g['counts'], pack_dets(g['counts'], g['dets']), True, 53)
+        _check(got, g['rows'])
+    rng = np.random.default_rng(21)
+    seq = random_detection_sequence(rng, n_frames=70, n_cells=900, width=1228., height=922., p_miss=0.05)
+    counts = np.array([len(s) for s in seq], np.int32)
+    lp = LinkerPort(max_disappeared=30.0, fps=30.0)
+    rows = []
+    for t, rec in enumerate(seq):
+        rects = [((float(r[0]), float(r[1])), (float(r[2]), float(r[3]), float(r[4]))) for r in rec]
+        rows += [(t, i, xy[0], xy[1], info[0], info[1], info[2]) for (i, xy, info) in lp.update(rects)]
+    got, live = _run(counts, pack_dets(counts, np.concatenate(seq)), True, 16)
+    _check(got, np.array(rows, np.float64))
+    assert live == (len(lp.ids), lp.next_id)

@@ -48,7 +48,7 @@ struct ysmr_ctx {
     int img_is_marker = 0;        // DIRECT on the marker image (dark-on-light quirk)
     int t_mask = 0, t_marker = 0, inverted = 0, signed_offset = 0;
     int window = 0;               // mean/std moving window (frames)
-    int link_fast = 1;            // YSMR_LINK=general disables the shared-memory fast path of the linker (tests)
+    int link_fast = 1;            // YSMR_LINK=general disables the lane fast path of the linker; ,grid / ,cta pick the general kernel (tests)
     int frontend_gen = 4;         // 3: force the three-kernel front-end (ysmr_set_option, A/B measurements in bench.py)
     cudaStream_t s_tail = nullptr; cudaEvent_t ev_tail_fork = nullptr, ev_tail_join = nullptr;   // K1b tail-strip launch
     uint8_t *plane = nullptr; int64_t plane_stride = 0; int pitch = 0;          // blurred planes (K1a -> K1b)
@@ -197,7 +197,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     ysmr_ctx *c = new ysmr_ctx();
     c->device = device; c->h = height; c->w = width; c->ww = (width + 31) / 32; c->channels = channels; c->p = *params;
     derive_thresholds(c);
-    { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strcmp(lk, "general") == 0); }
+    { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strstr(lk, "general")); }
 #define CC(expr)                                                                                                       \
     do {                                                                                                               \
         cudaError_t e__ = (expr);                                                                                      \
@@ -280,6 +280,8 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     CC(dev_alloc(c, &lf.cell_items, MB)); CC(dev_alloc(c, &lf.cell_start, (size_t)LINK_GRID_CELLS + 2)); CC(dev_alloc(c, &lf.flags, 4));
     CC(dev_alloc(c, &lx.lane_done, 1));
     CC(cudaMemset(lx.lane_done, 0, sizeof(int32_t)));
+    CC(dev_alloc(c, &lx.grid_ws, 8));
+    CC(cudaMemset(lx.grid_ws, 0, 8 * sizeof(int32_t)));
     {
         // detection grid of the general path: at most 32 x 32 cells of at least 16 pixels covering [0, W] x [0, H]
         const int ext = (width > height ? width : height) + 1;

@@ -71,6 +71,7 @@ struct LinkScratch {
     int prep_frames;                     // frames per sequential launch
     int32_t *lane_done;                  // [1] frames of the launch the fast path handled (read by link_general_kernel)
     float prep_margin;                   // float32 rounding bound of coordinates / distances (pixels)
+    int32_t *grid_ws;                    // [8] workspace of the cooperative-grid general path (link.cu: GridLinkCta), zeroed
 };
 
 struct RowOut {                          // must match ysmr_row (include/ysmr_b200.h)
