@@ -47,6 +47,7 @@ def parse():
     ap.add_argument('--multi', default='stream', choices=['stream', 'gather'],
                     help='N > 1: stream detection records chunk by chunk to the linker (default) or gather whole ranges')
     ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--ysmr-frames', type=int, default=600, help='frames of the FFV1 video of the drop-in leg (0: skip)')
     ap.add_argument('--no-cpu', action='store_true')
     args = ap.parse_args()
     setup_config(args)
@@ -231,6 +232,60 @@ def workload_text(args, channels, frames_per_gpu, world):
             f'{frames_per_gpu} frames per GPU x {world} GPU(s)' + (' of one video (strong scaling)' if args.strong else ''))
 
 
+def port_calibration():
+    """oracle/port_calibration.json (scripts/calibrate_port.py, build container): ms per frame of the real
+    ysmr.tracker.CentroidTracker + GaussianSumFIR over the restated tracker the CPU legs time."""
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'oracle', 'port_calibration.json')) as fh:
+            cal = json.load(fh)
+        return {k: round(v['reference_over_port'], 3) for k, v in cal['cases'].items()}
+    except Exception:
+        return None
+
+
+def ysmr_leg(args, frames, Cn, H, W):
+    """Wall time of the drop-in on a video FILE: what a YSMR user sees (reference: 19.6 frames/s for the same 300-frame
+    scene in the survey container, BASELINE.md section 2, of which FFV1 decode was 7.9 ms per frame)."""
+    import shutil
+    import tempfile
+
+    import cv2
+    from ysmr_b200.select import select_tracks
+    from ysmr_b200.track_eval import track_bacteria
+    n = min(args.ysmr_frames, frames.shape[0])
+    grey = (frames[:n, :, :, 0] if Cn == 3 else frames[:n]).cpu().numpy()
+    tmp = tempfile.mkdtemp(prefix='ysmr_b200_bench_')
+    try:
+        video = os.path.join(tmp, 'scene.avi')
+        vw = cv2.VideoWriter(video, cv2.VideoWriter_fourcc(*'FFV1'), 30.0, (W, H), True)
+        for f in grey:
+            vw.write(np.repeat(f[..., None], 3, axis=-1))
+        vw.release()
+        st = detect_settings(args)
+        settings = {'white bacteria on dark background': bool(st.white_on_dark), 'threshold offset for detection': int(st.offset),
+                    'adaptive double threshold': float(st.adt), 'minimal frame count': 10, 'display video analysis': False,
+                    'minimal length in seconds': 2.0, 'limit track length to x seconds': 2.0, 'store processed .csv file': True,
+                    'frame height': H, 'frame width': W}
+        out = {}
+        for sink in ('append', 'once'):
+            t0 = time.perf_counter()
+            res = track_bacteria(video, dict(settings), tmp, row_sink=sink, max_blobs=args.table['max_blobs'], max_tracks=args.table['max_tracks'])
+            t1 = time.perf_counter()
+            if res is None:
+                return {'error': 'track_bacteria returned None'}
+            df, fps, fh, fw, csv_path = res
+            sel = select_tracks(path_to_file=csv_path, df=df, results_directory=tmp, fps=fps, frame_height=fh, frame_width=fw,
+                                settings=dict(settings))
+            t2 = time.perf_counter()
+            out[sink] = {'track_s': t1 - t0, 'select_s': t2 - t1, 'rows': int(len(df)), 'selected_rows': 0 if sel is None else int(len(sel))}
+        best = min(out.values(), key=lambda v: v['track_s'] + v['select_s'])
+        return {'value': n / (best['track_s'] + best['select_s']), 'unit': 'frames/s', 'frames': n, 'container': 'FFV1 AVI (lossless, intra-only)',
+                'what': 'track_bacteria (cv2 decode on reader threads, GPU detect + link, sorted CSV) + select_tracks (GPU), wall clock',
+                'row_sink': out, 'host_cpus': os.cpu_count()}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 def run_reference(args):
     """--impl reference: rank 0 only; each step is a bounded sample (args.cpu_frames frames) of the same workload."""
     rank = int(os.environ.get('RANK', '0'))
@@ -260,8 +315,9 @@ def run_reference(args):
         'cpu_baseline': {'value': v, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                          'sample': f'{n} frames/step x {args.steps} steps; oracle = the reference loop body '
                                    f'(track_eval.py:180-316) on cv2/scipy + restated CentroidTracker/GSFF '
-                                   f'(speed of the restated tracker against the real class: BASELINE.md section 5); '
-                                   f'host has {os.cpu_count()} cpus'},
+                                   f'(speed of the restated tracker against the real class: port_vs_reference_tracker); '
+                                   f'host has {os.cpu_count()} cpus',
+                         'port_vs_reference_tracker': port_calibration()},
         'e2e': {'value': v, 'unit': 'frames/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -587,6 +643,15 @@ def main():
             # context with channels=1, so a third of the bytes cross PCIe (cv2.cvtColor is the identity when B == G == R)
             e2e_grey = e2e_leg(1)
 
+    # ---- e2e through the drop-in: ysmr_b200.track_eval.track_bacteria + select_tracks on a lossless FFV1 AVI of the scene
+    # (decode by cv2.VideoCapture reader threads -> pinned buffers -> ysmr_track_host -> sorted CSV -> GPU selection)
+    e2e_ysmr = None
+    if not args.no_e2e and world == 1 and args.ysmr_frames > 0:
+        try:
+            e2e_ysmr = ysmr_leg(args, frames, Cn, H, W)
+        except Exception as ex:          # the leg is a report beside the metric, never a reason to lose the line
+            e2e_ysmr = {'error': repr(ex)}
+
     # ---- CPU baseline on a bounded sample of the same bytes, and the parity check of the timed bytes ----------------------
     cpu = parity = None
     if not args.no_cpu and world == 1:
@@ -595,7 +660,8 @@ def main():
         fps_cpu, dt_cpu, ref_rows, threads = cpu_reference_fps(sample, detect_settings(args), keep_rows=True)
         cpu = {'value': fps_cpu, 'unit': 'frames/s', 'cores': threads, 'kind': 'port',
                'sample': f'first {S} frames of the same video, {dt_cpu:.1f} s; reference loop body (track_eval.py:180-316) '
-                         f'replayed on cv2/scipy + restated CentroidTracker/GSFF; host has {os.cpu_count()} cpus'}
+                         f'replayed on cv2/scipy + restated CentroidTracker/GSFF; host has {os.cpu_count()} cpus',
+               'port_vs_reference_tracker': port_calibration()}
         parity = parity_check(rows[rows['frame'] < S], ref_rows)
 
     line = {
@@ -611,7 +677,7 @@ def main():
                                    f'chunk-interleaved frame ranges x{world} ({B}-frame chunks, chunk c on rank c % {world}), '
                                    f'records streamed over NCCL to the one sequential linker on rank 0'),
                    'rows': n_rows, 'tracks': n_tracks, 'max_blobs': MB, 'max_tracks': MT},
-        'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': int(launches), 'clocks': clocks,
+        'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'e2e_ysmr': e2e_ysmr, 'gpu_launches': int(launches), 'clocks': clocks,
         'parity_check': parity,
     }
     if e2e_grey is not None:

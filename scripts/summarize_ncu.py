@@ -4,8 +4,8 @@
   python scripts/summarize_ncu.py launches gpurun_out/launches.csv profiles/r1_launches_summary.md "command line"
   python scripts/summarize_ncu.py full gpurun_out/prof.ncu-rep profiles/r1_ncu_full_summary.md "command line" [frames_per_launch]
 
-`full` also writes profiles/r1_traffic.json (DRAM bytes per frame of the front-end kernels) which bench.py reports as
-roofline.traffic.
+`full` also updates profiles/r2_traffic.json (DRAM bytes per frame of the front-end kernels, per configuration) which
+bench.py reports as roofline.traffic.
 """
 import collections
 import csv
@@ -32,8 +32,9 @@ def launches(src, dst, cmd):
                 name = d['Kernel Name']
                 agg[name].append(v)
                 geo[name] = (d.get('Grid Size', ''), d.get('Block Size', ''))
-    names = ('blur_prepass', 'plane_margins', 'gauss_decide', 'pack_masks', 'label_kernel', 'geometry', 'link_kernel', 'link_reset',
-             'scalar_decide', 'frame_moments', 'moving_threshold', 'frontend_tile', 'unpack_bits')
+    names = ('fused_front', 'blur_prepass', 'plane_margins', 'gauss_decide', 'pack_masks', 'label_kernel', 'geometry', 'link_kernel',
+             'link_prep', 'link_general', 'link_reset', 'scalar_decide', 'frame_moments', 'moving_threshold', 'frontend_tile',
+             'unpack_bits', 'rows_', 'select_')
     ours = {k: v for k, v in agg.items() if OURS in k or k.startswith('void ysmr') or any(n in k for n in names)}
     total = sum(sum(v) for v in ours.values())
     with open(dst, 'w') as f:
@@ -63,7 +64,7 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__icc_request_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct']
 
 
-def full(src, dst, cmd, frames_per_launch):
+def full(src, dst, cmd, frames_per_launch, config='cfg2'):
     raw = subprocess.run(['ncu', '-i', src, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
@@ -102,10 +103,13 @@ def full(src, dst, cmd, frames_per_launch):
             f.write('\n')
     if frames_per_launch and traffic:
         per = {k: sum(v) / len(v) for k, v in traffic.items()}
-        fe = sum(v for k, v in per.items() if any(t in k for t in ('blur_prepass', 'plane_margins', 'gauss_decide', 'pack_masks')))
-        out = {'frames_per_launch': frames_per_launch, 'dram_bytes_per_frame': per, 'frontend_dram_bytes_per_frame': fe,
-               'source': os.path.basename(dst)}
-        json.dump(out, open(os.path.join(os.path.dirname(dst), 'r1_traffic.json'), 'w'), indent=1)
+        fe = sum(v for k, v in per.items() if any(t in k for t in ('fused_front', 'blur_prepass', 'plane_margins', 'gauss_decide', 'pack_masks')))
+        # bench.py reads profiles/r2_traffic.json: front-end DRAM bytes per frame, per configuration
+        path = os.path.join(os.path.dirname(dst), 'r2_traffic.json')
+        out = json.load(open(path)) if os.path.isfile(path) else {'frontend_dram_bytes_per_frame': {}, 'detail': {}}
+        out['frontend_dram_bytes_per_frame'][config] = fe
+        out['detail'][config] = {'frames_per_launch': frames_per_launch, 'dram_bytes_per_frame': per, 'source': os.path.basename(dst)}
+        json.dump(out, open(path, 'w'), indent=1)
     print(open(dst).read()[:6000])
 
 
@@ -114,4 +118,4 @@ if __name__ == '__main__':
     if mode == 'launches':
         launches(src, dst, cmd)
     else:
-        full(src, dst, cmd, int(sys.argv[5]) if len(sys.argv) > 5 else 0)
+        full(src, dst, cmd, int(sys.argv[5]) if len(sys.argv) > 5 else 0, sys.argv[6] if len(sys.argv) > 6 else 'cfg2')

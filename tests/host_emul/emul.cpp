@@ -125,6 +125,10 @@ struct HostLinkCta : HostCta {
     void atomic_min_i32(int32_t *p, int32_t v) const { if (v < *p) *p = v; }
     uint32_t atomic_add_u32(uint32_t *p, uint32_t v) const { const uint32_t o = *p; *p = o + v; return o; }
     bool any(int v) const { return v != 0; }
+    void stage_detections(const LinkConfig &c, const LinkScratch &x, const FrameScratch &f, const float *dets, int m, DetGrid &G)
+    {
+        stage_detections_generic(*this, c, x, f, dets, m, G);
+    }
 };
 
 struct HostLinker {

@@ -40,6 +40,8 @@ struct Control {             // small device block, zeroed per detect call where
 
 }  // namespace
 
+constexpr int GATE_FLAGS = 1024;     // chunks per ysmr_track_* call that can use the gated linker launch
+
 struct ysmr_ctx {
     int device = 0, h = 0, w = 0, ww = 0, channels = 1;
     ysmr_params p{};
@@ -48,6 +50,8 @@ struct ysmr_ctx {
     int img_is_marker = 0;        // DIRECT on the marker image (dark-on-light quirk)
     int t_mask = 0, t_marker = 0, inverted = 0, signed_offset = 0;
     int window = 0;               // mean/std moving window (frames)
+    int32_t *gate_flags = nullptr;   // [GATE_FLAGS] "detections of chunk k are ready" (track_chunks / LinkGate)
+    int link_gate = 1;               // YSMR_LINK=...,nogate: sequence linker launches behind detection with events only
     int link_fast = 1;            // YSMR_LINK=general disables the lane fast path of the linker; ,grid / ,cta pick the general kernel (tests)
     int frontend_gen = 4;         // 3: force the three-kernel front-end (ysmr_set_option, A/B measurements in bench.py)
     cudaStream_t s_tail = nullptr; cudaEvent_t ev_tail_fork = nullptr, ev_tail_join = nullptr;   // K1b tail-strip launch
@@ -197,7 +201,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     ysmr_ctx *c = new ysmr_ctx();
     c->device = device; c->h = height; c->w = width; c->ww = (width + 31) / 32; c->channels = channels; c->p = *params;
     derive_thresholds(c);
-    { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strstr(lk, "general")); }
+    { const char *lk = getenv("YSMR_LINK"); c->link_fast = !(lk && strstr(lk, "general")); c->link_gate = !(lk && strstr(lk, "nogate")); }
 #define CC(expr)                                                                                                       \
     do {                                                                                                               \
         cudaError_t e__ = (expr);                                                                                      \
@@ -293,8 +297,10 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     lx.set_table_size = set_table_capacity((int)MB);
     CC(dev_alloc(c, &lx.table, (size_t)lx.set_table_size));
     lx.prep_frames = 4096;
-    CC(dev_alloc(c, &lx.succ, (size_t)lx.prep_frames * 256));
-    CC(dev_alloc(c, &lx.thr2, (size_t)lx.prep_frames * 256));
+    CC(dev_alloc(c, &lx.succ, (size_t)2 * lx.prep_frames * 256));          // two halves: pipelined launches alternate (LinkGate)
+    CC(dev_alloc(c, &lx.thr2, (size_t)2 * lx.prep_frames * 256));
+    CC(dev_alloc(c, &c->gate_flags, (size_t)GATE_FLAGS));
+    CC(cudaMemset(c->gate_flags, 0, GATE_FLAGS * sizeof(int32_t)));
     lx.prep_margin = 2.0e-3f + 1.0e-6f * (float)(height + width);
     CC(dev_alloc(c, &c->phase_cycles, 16));
     CC(cudaMemset(c->phase_cycles, 0, 16 * sizeof(long long)));
@@ -484,14 +490,15 @@ static int link_ready(ysmr_ctx *c)
 }
 
 static int link_impl(ysmr_ctx *c, const int32_t *d_blob_count, const float *d_blobs, int first_frame, int n_frames,
-                     ysmr_row *d_rows, int64_t rows_capacity, int64_t *d_n_rows, int append, cudaStream_t st)
+                     ysmr_row *d_rows, int64_t rows_capacity, int64_t *d_n_rows, int append, cudaStream_t st,
+                     const LinkGate *gate = nullptr)
 {
     LinkIo io{};
     io.blob_count = d_blob_count; io.blobs = d_blobs; io.rows = (RowOut *)d_rows; io.rows_capacity = rows_capacity;
     io.n_rows = (long long *)d_n_rows; io.append = append;
     io.status = &c->ctl->status; io.first_bad = &c->ctl->first_bad;
     ProfScope ps(c, YSMR_PROF_LINK, st);
-    CU(c, launch_link(c->lc, c->ls, c->lx, c->lf, io, first_frame, n_frames, c->link_fast, st));
+    CU(c, launch_link(c->lc, c->ls, c->lx, c->lf, io, first_frame, n_frames, c->link_fast, st, gate));
     c->launches += (c->link_fast) ? 3 * ((n_frames + c->lx.prep_frames - 1) / c->lx.prep_frames) : 1;
     return YSMR_OK;
 }
@@ -602,19 +609,27 @@ static int track_chunks(ysmr_ctx *c, const uint8_t *frames, bool host_frames, in
         c->stage_bytes = frame_bytes * (size_t)B;
         for (int i = 0; i < 2; ++i) CU(c, cudaMalloc((void **)&c->stage[i], c->stage_bytes));
     }
+    // Gated linker launches (LinkGate, link.cuh): the linker of chunk k is enqueued without waiting for the chunk's detection
+    // and spins on gate_flags[k], which a memset behind the chunk's detection kernels sets.  Not while per-kernel timing is on
+    // (the event bracket would time the spinning).
+    const bool gated = c->link_gate && c->link_fast && !c->profiling && B <= c->lx.prep_frames;
+    if (gated) CU(c, cudaMemsetAsync(c->gate_flags, 0, GATE_FLAGS * sizeof(int32_t), user));
     CU(c, cudaEventRecord(c->ev_fork, user));
     CU(c, cudaStreamWaitEvent(c->s_copy, c->ev_fork, 0));
     CU(c, cudaStreamWaitEvent(c->s_det, c->ev_fork, 0));
     CU(c, cudaStreamWaitEvent(c->s_link, c->ev_fork, 0));
     CU(c, cudaMemsetAsync(d_n_rows, 0, sizeof(int64_t), c->s_link));
-    // Chunk schedule: full batches while plenty of frames are left, then chunks that shrink geometrically (each 45 % of what
-    // is left; measured best of three schedules).  The linker of chunk i runs beside the detection of chunk i+1, so whatever the linker still has to do when
+    // Chunk schedule: a doubling lead-in, full batches while plenty of frames are left, then chunks that shrink geometrically
+    // (each 45 % of what is left; measured best of three schedules).  The linker of chunk i runs beside the detection of chunk i+1, so whatever the linker still has to do when
     // the last detection finishes is exposed; with shrinking chunks it has caught up by then (a uniform schedule leaves the
     // link time of about one full batch as a tail).
     int chunk = 0;
     for (int f0 = 0, nf = 0; f0 < n_frames; f0 += nf, ++chunk) {
         const int rem = n_frames - f0;
         nf = std::min(B, std::max(96, (int)(0.45 * rem + 0.5)));
+        // lead-in: the first chunks double from an eighth of a batch, so that the sequential linker -- the longer of the two
+        // pipelines at ~50 tracks per frame -- starts after a fraction of a batch's detection time instead of a whole one
+        if (chunk < 3) nf = std::min(nf, std::max(32, B / 8) << chunk);
         if (nf > rem || rem - nf < 48) nf = std::min(rem, B);
         const int b = chunk & 1;
         const uint8_t *src = frames + (size_t)f0 * frame_stride;
@@ -637,9 +652,18 @@ static int track_chunks(ysmr_ctx *c, const uint8_t *frames, bool host_frames, in
         int r = ysmr_detect(c, dfr, nf, dstride, first_frame + f0, c->pipe_count[b], c->pipe_blobs[b], nullptr, c->s_det);
         if (r) return r;
         CU(c, cudaEventRecord(c->ev_det[b], c->s_det));
-        CU(c, cudaStreamWaitEvent(c->s_link, c->ev_det[b], 0));
-        r = link_impl(c, c->pipe_count[b], c->pipe_blobs[b], first_frame + f0, nf, d_rows, rows_capacity, d_n_rows, 1, c->s_link);
-        if (r) return r;
+        if (gated && chunk < GATE_FLAGS) {
+            const LinkGate gate{c->gate_flags + chunk, c->s_det, b};
+            r = link_impl(c, c->pipe_count[b], c->pipe_blobs[b], first_frame + f0, nf, d_rows, rows_capacity, d_n_rows, 1, c->s_link, &gate);
+            // (set even if the launch above failed: a linker kernel that did get enqueued must not spin until its time-out)
+            cudaMemsetAsync(c->gate_flags + chunk, 1, sizeof(int32_t), c->s_det);
+            if (r) return r;
+            CU(c, cudaEventRecord(c->ev_det[b], c->s_det));
+        } else {
+            CU(c, cudaStreamWaitEvent(c->s_link, c->ev_det[b], 0));
+            r = link_impl(c, c->pipe_count[b], c->pipe_blobs[b], first_frame + f0, nf, d_rows, rows_capacity, d_n_rows, 1, c->s_link);
+            if (r) return r;
+        }
         CU(c, cudaEventRecord(c->ev_link[b], c->s_link));
     }
     CU(c, cudaEventRecord(c->ev_join, c->s_link));

@@ -32,6 +32,9 @@
 //   2b  column pass (3 IDP per 2 x 2 group) -> per-group threshold byte -> candidate test -> candidate list
 //   3   exact float32 Gaussian + both decisions for the candidates -> bits into the shared mask tiles
 //   4   mask tiles -> HBM (the only global stores of the kernel: 2 bits per pixel)
+#include <stdlib.h>
+#include <string.h>
+
 #include "frontend.cuh"
 #include "front_arith.cuh"
 
@@ -181,7 +184,12 @@ __host__ __device__ constexpr int fused_gp(int tw)
     return gp;
 }
 
-template <int C, int LTW>
+// CS: the input pixels are read exactly once -- cache-streaming loads (ld.global.cs, evict-first in L2) keep them from
+// pushing the masks, detection records and linker tables of the other kernels out of the 126 MB L2.
+template <bool CS>
+__device__ __forceinline__ uint32_t ld_px(const uint32_t *q) { return CS ? __ldcs(q) : __ldg(q); }
+
+template <int C, int LTW, bool CS>
 __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams p, FusedGeom g)
 {
     const int tid = threadIdx.x, lane = tid & 31;
@@ -228,8 +236,8 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
                 if (!y_inside) gy = reflect101(gy, H);
                 const uint8_t *rowp = frame + gy * rowstride;
                 const uint32_t *qa = reinterpret_cast<const uint32_t *>(rowp + offa), *qb = reinterpret_cast<const uint32_t *>(rowp + offb);
-                raw[0][0] = __ldg(qa); raw[1][0] = __ldg(qb);
-                if (C == 3) { raw[0][1] = __ldg(qa + 1); raw[0][2] = __ldg(qa + 2); raw[1][1] = __ldg(qb + 1); raw[1][2] = __ldg(qb + 2); }
+                raw[0][0] = ld_px<CS>(qa); raw[1][0] = ld_px<CS>(qb);
+                if (C == 3) { raw[0][1] = ld_px<CS>(qa + 1); raw[0][2] = ld_px<CS>(qa + 2); raw[1][1] = ld_px<CS>(qb + 1); raw[1][2] = ld_px<CS>(qb + 2); }
             };
             auto store = [&](const uint32_t (&raw)[2][C == 3 ? 3 : 1]) {
                 const uint32_t va = C == 3 ? grey4_of_bgr(raw[0][0], raw[0][1], raw[0][2]) : raw[0][0];
@@ -246,8 +254,8 @@ __global__ void __launch_bounds__(FT_THREADS, 3) fused_front_kernel(FrontParams 
                 const int64_t dab = offb - offa, adv = rstep * rowstride;
                 auto ld = [&](Raw &raw) {
                     const uint32_t *qa = reinterpret_cast<const uint32_t *>(pa), *qb = reinterpret_cast<const uint32_t *>(pa + dab);
-                    raw[0][0] = __ldg(qa); raw[1][0] = __ldg(qb);
-                    if (C == 3) { raw[0][1] = __ldg(qa + 1); raw[0][2] = __ldg(qa + 2); raw[1][1] = __ldg(qb + 1); raw[1][2] = __ldg(qb + 2); }
+                    raw[0][0] = ld_px<CS>(qa); raw[1][0] = ld_px<CS>(qb);
+                    if (C == 3) { raw[0][1] = ld_px<CS>(qa + 1); raw[0][2] = ld_px<CS>(qa + 2); raw[1][1] = ld_px<CS>(qb + 1); raw[1][2] = ld_px<CS>(qb + 2); }
                     pa += adv;
                 };
                 const int cnt = (n_rows - r0 + rstep - 1) / rstep;       // rows of this thread (>= 3: th >= 16)
@@ -578,13 +586,34 @@ bool fused_frontend_supported(const FrontParams &p)
 }
 
 // per device (the attribute is per device / context): called from ysmr_create
+template <int C, int LTW, bool CS>
+static cudaError_t fused_attr()
+{
+    return cudaFuncSetAttribute(fused_front_kernel<C, LTW, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+}
 cudaError_t fused_frontend_init()
 {
-    cudaError_t e = cudaFuncSetAttribute(fused_front_kernel<1, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_front_kernel<1, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_front_kernel<3, 7>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(fused_front_kernel<3, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024);
+    cudaError_t e = fused_attr<1, 7, false>();
+    if (e == cudaSuccess) e = fused_attr<1, 8, false>();
+    if (e == cudaSuccess) e = fused_attr<3, 7, false>();
+    if (e == cudaSuccess) e = fused_attr<3, 8, false>();
+    if (e == cudaSuccess) e = fused_attr<1, 7, true>();
+    if (e == cudaSuccess) e = fused_attr<1, 8, true>();
+    if (e == cudaSuccess) e = fused_attr<3, 7, true>();
+    if (e == cudaSuccess) e = fused_attr<3, 8, true>();
     return e;
+}
+
+template <bool CS>
+static void launch_fused_cs(const FrontParams &p, const FusedGeom &g, dim3 grid, cudaStream_t st)
+{
+    if (p.channels == 3) {
+        if (g.ltw == 8) fused_front_kernel<3, 8, CS><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
+        else fused_front_kernel<3, 7, CS><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
+    } else {
+        if (g.ltw == 8) fused_front_kernel<1, 8, CS><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
+        else fused_front_kernel<1, 7, CS><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
+    }
 }
 
 cudaError_t launch_fused_frontend(const FrontParams &p, cudaStream_t st)
@@ -592,13 +621,9 @@ cudaError_t launch_fused_frontend(const FrontParams &p, cudaStream_t st)
     const FusedGeom g = fused_geometry(p);
     if (g.tiles_y > 65535 || p.n_frames > 65535 || g.smem_bytes > 100 * 1024 || g.gp != fused_gp(g.tw)) return cudaErrorInvalidConfiguration;
     const dim3 grid((unsigned)g.tiles_x, (unsigned)g.tiles_y, (unsigned)p.n_frames);
-    if (p.channels == 3) {
-        if (g.ltw == 8) fused_front_kernel<3, 8><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
-        else fused_front_kernel<3, 7><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
-    } else {
-        if (g.ltw == 8) fused_front_kernel<1, 8><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
-        else fused_front_kernel<1, 7><<<grid, FT_THREADS, g.smem_bytes, st>>>(p, g);
-    }
+    static const bool plain_loads = [] { const char *e = getenv("YSMR_FUSED_LOADS"); return e && strcmp(e, "ldg") == 0; }();
+    if (plain_loads) launch_fused_cs<false>(p, g, grid, st);     // (measurement: the A/B of the streaming loads)
+    else launch_fused_cs<true>(p, g, grid, st);
     return cudaGetLastError();
 }
 

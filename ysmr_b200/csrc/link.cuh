@@ -81,7 +81,7 @@ struct RowOut {                          // must match ysmr_row (include/ysmr_b2
     int32_t pad;
 };
 
-enum { LINK_ST_TRACK_OVERFLOW = 8, LINK_ST_ROW_OVERFLOW = 16 };
+enum { LINK_ST_TRACK_OVERFLOW = 8, LINK_ST_ROW_OVERFLOW = 16, LINK_ST_GATE_TIMEOUT = 32 };
 
 YSMR_HD unsigned long long f64_bits(double v)
 {
@@ -521,6 +521,36 @@ struct FrameScratch {
 
 constexpr int LINK_GRID_CELLS = 1024;    // at most 32 x 32 cells
 
+// Staging of a frame's detections for the general path: centres into f.dxy, claim slots reset, detections binned into the
+// uniform grid by a counting sort over cells.  On return G points at the grid and every thread may search it.
+template <class Cta>
+YSMR_HD void stage_detections_generic(Cta &cta, const LinkConfig &c, const LinkScratch &x, const FrameScratch &f, const float *dets,
+                                      int m, DetGrid &G)
+{
+    const int tid = cta.tid(), nthr = cta.nthr();
+    const int NONE = 0x7fffffff;
+    G.dxy = f.dxy; G.cell_start = f.cell_start; G.cell_items = f.cell_items;
+    const int ncell = G.gw * G.gh;
+    for (int k = tid; k <= ncell; k += nthr) f.cell_start[k] = 0;
+    if (tid == 0) f.flags[0] = 0;
+    cta.sync();
+    for (int q = tid; q < m; q += nthr) {
+        float2 d; d.x = dets[5 * q]; d.y = dets[5 * q + 1];
+        f.dxy[q] = d;
+        f.col_best[q] = ~0ull;
+        const int cell = grid_coord((double)d.y, G.inv_cell, G.gh) * G.gw + grid_coord((double)d.x, G.inv_cell, G.gw);
+        x.flag[q] = (uint32_t)cell;
+        f.col_row[q] = (int32_t)cta.atomic_add_u32(&f.cell_start[cell], 1u);   // position within the cell
+    }
+    cta.sync();
+    cta.exclusive_scan(f.cell_start, ncell + 1);
+    for (int q = tid; q < m; q += nthr) {
+        f.cell_items[f.cell_start[x.flag[q]] + (uint32_t)f.col_row[q]] = q;
+        f.col_row[q] = NONE;
+    }
+    cta.sync();
+}
+
 // Processes frames [start_frame, n_frames) of the chunk.  One CTA; within a frame the phases are loops over tracks or
 // detections separated by cta.sync().  Header values live in registers of every thread and are updated identically by all
 // of them (every quantity they depend on is CTA-uniform), thread 0 writes them back at the end.  Track state is
@@ -554,29 +584,11 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
             for (int q = tid; q < m; q += nthr) x.list[q] = q;              // detection order (tracker.py:135-137)
             cta.sync();
         } else {
-            // ---- stage the detections and bin them into the grid (counting sort over cells)
+            // ---- stage the detections and bin them into the grid (counting sort over cells): the Cta policy decides where
+            // the grid lives (stage_detections_generic below; a cooperative grid builds a private copy per block)
             DetGrid G;
-            G.dxy = f.dxy; G.cell_start = f.cell_start; G.cell_items = f.cell_items;
             G.cell = c.grid_cell; G.inv_cell = 1.0 / c.grid_cell; G.gw = c.grid_w; G.gh = c.grid_h;
-            const int ncell = G.gw * G.gh;
-            for (int k = tid; k <= ncell; k += nthr) f.cell_start[k] = 0;
-            if (tid == 0) f.flags[0] = 0;
-            cta.sync();
-            for (int q = tid; q < m; q += nthr) {
-                float2 d; d.x = dets[5 * q]; d.y = dets[5 * q + 1];
-                f.dxy[q] = d;
-                f.col_best[q] = ~0ull;
-                const int cell = grid_coord((double)d.y, G.inv_cell, G.gh) * G.gw + grid_coord((double)d.x, G.inv_cell, G.gw);
-                x.flag[q] = (uint32_t)cell;
-                f.col_row[q] = (int32_t)cta.atomic_add_u32(&f.cell_start[cell], 1u);   // position within the cell
-            }
-            cta.sync();
-            cta.exclusive_scan(f.cell_start, ncell + 1);
-            for (int q = tid; q < m; q += nthr) {
-                f.cell_items[f.cell_start[x.flag[q]] + (uint32_t)f.col_row[q]] = q;
-                f.col_row[q] = NONE;
-            }
-            cta.sync();
+            cta.stage_detections(c, x, f, dets, m, G);
             // ---- nearest detection of every track (cdist row minimum / first argmin, tracker.py:151-163) and its claim
             for (int r = tid; r < n; r += nthr) {
                 const int slot = order[r];
@@ -700,8 +712,18 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
 }
 
 #if defined(__CUDACC__)
+// Gate of a pipelined launch (capi.cu: track_chunks): the sequential kernel is enqueued BEFORE the detections it will
+// read exist and spins on *ready (set by a memset behind the detection kernels of the chunk), so that it keeps the SM it
+// runs on from chunk to chunk instead of having to wait, every chunk, for an SM that the detection kernels of the next
+// chunk have completely vacated.  The candidate tables are then built on the detection stream (`prep_stream`), into half
+// `table` of the double-buffered table memory.
+struct LinkGate {
+    const int32_t *ready;
+    cudaStream_t prep_stream;
+    int table;
+};
 cudaError_t launch_link(const LinkConfig &c, const LinkState &s, const LinkScratch &x, const FrameScratch &f, const LinkIo &io,
-                        int first_frame, int n_frames, int allow_fast, cudaStream_t st);
+                        int first_frame, int n_frames, int allow_fast, cudaStream_t st, const LinkGate *gate = nullptr);
 cudaError_t launch_link_reset(const LinkState &s, int max_tracks, cudaStream_t st);
 cudaError_t link_kernel_init();            // per device: shared-memory opt-in of the linker kernels (from ysmr_create)
 #endif
