@@ -296,7 +296,7 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
     CC(dev_alloc(c, &lx.flag, std::max(T, MB) + 2)); CC(dev_alloc(c, &lx.list, MB));
     lx.set_table_size = set_table_capacity((int)MB);
     CC(dev_alloc(c, &lx.table, (size_t)lx.set_table_size));
-    lx.prep_frames = 4096;
+    lx.prep_frames = 2048;           // = FAST_FRAMES of link.cu
     CC(dev_alloc(c, &lx.succ, (size_t)2 * lx.prep_frames * 256));          // two halves: pipelined launches alternate (LinkGate)
     CC(dev_alloc(c, &lx.thr2, (size_t)2 * lx.prep_frames * 256));
     CC(dev_alloc(c, &c->gate_flags, (size_t)GATE_FLAGS));
