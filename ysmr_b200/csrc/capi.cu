@@ -653,12 +653,13 @@ static int track_chunks(ysmr_ctx *c, const uint8_t *frames, bool host_frames, in
         if (r) return r;
         CU(c, cudaEventRecord(c->ev_det[b], c->s_det));
         if (gated && chunk < GATE_FLAGS) {
-            const LinkGate gate{c->gate_flags + chunk, c->s_det, b};
-            r = link_impl(c, c->pipe_count[b], c->pipe_blobs[b], first_frame + f0, nf, d_rows, rows_capacity, d_n_rows, 1, c->s_link, &gate);
-            // (set even if the launch above failed: a linker kernel that did get enqueued must not spin until its time-out)
-            cudaMemsetAsync(c->gate_flags + chunk, 1, sizeof(int32_t), c->s_det);
-            if (r) return r;
+            // order of submission: tables, flag, and only then the kernel that waits for the flag (LinkGate, link.cuh)
+            CU(c, launch_link_prep(c->lc, c->lx, c->pipe_count[b], c->pipe_blobs[b], nf, b, c->s_det)); c->launches++;
+            CU(c, cudaMemsetAsync(c->gate_flags + chunk, 1, sizeof(int32_t), c->s_det));
             CU(c, cudaEventRecord(c->ev_det[b], c->s_det));
+            const LinkGate gate{c->gate_flags + chunk, b};
+            r = link_impl(c, c->pipe_count[b], c->pipe_blobs[b], first_frame + f0, nf, d_rows, rows_capacity, d_n_rows, 1, c->s_link, &gate);
+            if (r) return r;
         } else {
             CU(c, cudaStreamWaitEvent(c->s_link, c->ev_det[b], 0));
             r = link_impl(c, c->pipe_count[b], c->pipe_blobs[b], first_frame + f0, nf, d_rows, rows_capacity, d_n_rows, 1, c->s_link);

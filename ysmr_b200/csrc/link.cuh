@@ -715,13 +715,17 @@ YSMR_HD void link_chunk(Cta &cta, const LinkConfig &c, const LinkState &s, const
 // Gate of a pipelined launch (capi.cu: track_chunks): the sequential kernel is enqueued BEFORE the detections it will
 // read exist and spins on *ready (set by a memset behind the detection kernels of the chunk), so that it keeps the SM it
 // runs on from chunk to chunk instead of having to wait, every chunk, for an SM that the detection kernels of the next
-// chunk have completely vacated.  The candidate tables are then built on the detection stream (`prep_stream`), into half
-// `table` of the double-buffered table memory.
+// chunk have completely vacated.  The candidate tables are then built on the detection stream (launch_link_prep), into half
+// `table` of the double-buffered table memory.  The caller enqueues, in this order: detection, launch_link_prep, the memset
+// of the flag, and only then launch_link -- so that even a tool that serialises kernels (ncu) never runs the waiting kernel
+// before the work it waits for has been submitted.
 struct LinkGate {
     const int32_t *ready;
-    cudaStream_t prep_stream;
     int table;
 };
+// the candidate tables of a gated launch, on the detection stream (before the flag is set; launch_link then skips them)
+cudaError_t launch_link_prep(const LinkConfig &c, const LinkScratch &x, const int32_t *blob_count, const float *blobs, int n_frames,
+                             int table, cudaStream_t st);
 cudaError_t launch_link(const LinkConfig &c, const LinkState &s, const LinkScratch &x, const FrameScratch &f, const LinkIo &io,
                         int first_frame, int n_frames, int allow_fast, cudaStream_t st, const LinkGate *gate = nullptr);
 cudaError_t launch_link_reset(const LinkState &s, int max_tracks, cudaStream_t st);
