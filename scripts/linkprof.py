@@ -17,9 +17,16 @@ cs=[];bs=[]
 for a in range(0,F,256):
     c,b=ctx.detect(fr[a:a+256],a); cs.append(c); bs.append(b)
 counts=torch.cat(cs); blobs=torch.cat(bs)
+HOG=bool(os.environ.get('LINKPROF_HOG'))
+big=torch.empty(1<<30,dtype=torch.uint8,device='cuda') if HOG else None
+big2=torch.empty_like(big) if HOG else None
+side=torch.cuda.Stream()
 for rep in range(2):
     ctx.reset(); ctx.set_profiling(True, link_phases=not PLAIN)
     torch.cuda.synchronize()
+    if HOG:
+        with torch.cuda.stream(side):
+            for _ in range(60): big2.copy_(big)
     e0=torch.cuda.Event(enable_timing=True); e1=torch.cuda.Event(enable_timing=True)
     e0.record(); rows=ctx.link(counts,blobs,0,F*(3000 if CFG=='cfg3' else 400)); e1.record(); torch.cuda.synchronize()
     pc=ctx.link_phase_cycles()
