@@ -27,16 +27,25 @@ for a in range(0, F, 148):
 counts = torch.cat(cs); blobs = torch.cat(bs)
 torch.cuda.synchronize()
 hog = len(sys.argv) > 3 and sys.argv[3] == 'hog'
+mm = len(sys.argv) > 3 and sys.argv[3] == 'mm'
+ma = torch.randn(8192, 8192, device='cuda', dtype=torch.bfloat16) if mm else None
 big = torch.empty(1 << 30, dtype=torch.uint8, device='cuda') if hog else None
 big2 = torch.empty_like(big) if hog else None
 side = torch.cuda.Stream()
 for rep in range(3):
     ctx.reset(); ctx.set_profiling(True); ctx.get_profile()
+    if mm:                       # compute-bound GEMMs on the other SMs (little memory traffic)
+        with torch.cuda.stream(side):
+            for _ in range(40):
+                torch.mm(ma, ma)
     if hog:                      # a DRAM-streaming copy on another stream for the whole duration of the link (memory contention)
         with torch.cuda.stream(side):
             for _ in range(40):
                 big2.copy_(big)
-    rows = ctx.link(counts, blobs, 0, F * (3000 if name == 'cfg3' else 400))
+    try:
+        rows = ctx.link(counts, blobs, 0, int(os.environ.get('LINK_ROWS_CAP', F * (3000 if name == 'cfg3' else 400))))
+    except Exception as ex:          # (LINK_ROWS_CAP=1: the row overflow is the point -- no row is stored)
+        rows = []
     p = ctx.get_profile()['link']
     torch.cuda.synchronize()
-    print(f'{name}: link {"beside a 1 GB copy loop" if hog else "alone"} {p[0]:.3f} ms for {F} frames = {1e3 * p[0] / F:.3f} us/frame ({p[1]} profiled launches), rows {len(rows)}')
+    print(f'{name}: link {"beside a 1 GB copy loop" if hog else ("beside bf16 GEMMs" if mm else "alone")} {p[0]:.3f} ms for {F} frames = {1e3 * p[0] / F:.3f} us/frame ({p[1]} profiled launches), rows {len(rows)}')
