@@ -65,7 +65,8 @@ typedef struct ysmr_params {
     int32_t max_batch;       /* capacity: frames per ysmr_detect call                                     */
     double  max_distance;    /* association gate; <= 0 means off.  The reference has NO gate
                                 (tracker.py:171-177), so anything but off diverges from it.              */
-    int32_t reserved[4];
+    int32_t reserved[4];     /* reserved[0] > 0: explicit GSFF horizons n_i[0..n_f-1] (gsff.py:103-106 evaluated by the host
+                                with a FLOAT n_max when 'maximum horizon size' is unset, tracker.py:58-59); else n_min/n_max */
 } ysmr_params;
 
 #define YSMR_MAX_FILTERS 4

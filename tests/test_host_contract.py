@@ -27,3 +27,10 @@ def test_integration_doc_lists_every_exported_symbol():
 def test_header_cites_the_reference_for_every_entry_point():
     header = open(os.path.join(ROOT, 'include', 'ysmr_b200.h')).read()
     assert header.count('.py:') >= 10                        # file:line citations of the reference interface replaced
+
+
+def test_horizons_follow_the_reference_operand_types():
+    """gsff.py:103-106 with n_max = the float fps (tracker.py:58-59): int(fps) would give other horizons."""
+    from ysmr_b200.api import horizon_sizes
+    assert horizon_sizes(0, 30, 3) == [10, 20, 30] and horizon_sizes(0, 30.0, 3) == [10, 20, 30]
+    assert horizon_sizes(0, 29.97, 4) == [7, 14, 22, 29] and horizon_sizes(0, 29, 4) == [7, 14, 21, 29]

@@ -59,6 +59,12 @@ class Context:
         p.white_on_dark = int(bool(white_on_dark)); p.offset = int(offset); p.adt = float(adt); p.fps = float(fps)
         p.use_gsff = int(bool(use_gsff)); p.n_f = int(n_f); p.n_min = int(n_min)
         p.n_max = int(fps if n_max is None else n_max)          # tracker.py:58-59
+        # The horizons themselves come from the reference's expression on the reference's operand types (gsff.py:103-106):
+        # with 'maximum horizon size' unset n_max is the FLOAT fps (29.97 fps, four filters: 7, 14, 22, 29 -- int(fps) = 29
+        # would give 7, 14, 21, 29)
+        self.horizons = horizon_sizes(p.n_min, fps if n_max is None else n_max, p.n_f) if p.use_gsff else []
+        for i, n in enumerate(self.horizons[:4]):
+            p.reserved[i] = int(n)
         for key, val in (('max_blobs', max_blobs), ('max_tracks', max_tracks), ('max_runs', max_runs),
                          ('max_batch', max_batch)):
             if val is not None:
@@ -72,7 +78,7 @@ class Context:
         if rc != 0:
             raise YsmrError(rc, self.lib.ysmr_last_error(None).decode())
         if p.use_gsff:
-            for i, n in enumerate(horizon_sizes(p.n_min, p.n_max, p.n_f)):
+            for i, n in enumerate(self.horizons):
                 g = lsf_gain(n, 1 / p.fps)
                 self._check(self.lib.ysmr_set_gsff_gain(self._h, i, n, g.ctypes.data_as(C.c_void_p)))
 

@@ -253,6 +253,8 @@ int ysmr_create(ysmr_ctx **out, int device, int height, int width, int channels,
         const double step = (double)(params->n_max - params->n_min) / (double)params->n_f;      // gsff.py:103-106
         for (int i = 0; i < params->n_f; ++i) {
             lc.n_i[i] = (int)((double)params->n_min + step * (double)(i + 1));
+            // explicit horizons (ysmr_params::reserved): the host evaluated the reference's expression on its operand types
+            if (params->reserved[0] > 0 && i < 4) lc.n_i[i] = params->reserved[i];
             if (lc.n_i[i] < 1 || lc.n_i[i] > YSMR_MAX_HORIZON) {
                 fail(nullptr, YSMR_E_INVALID, "GSFF horizon out of range (1..64)");
                 ysmr_destroy(c);
