@@ -138,13 +138,24 @@ def track_streamed(n_frames, chunk, world, rank, detect_range, link_range, lead_
             r.wait()
         return None
     assert max_blobs is not None, 'rank 0 needs the record width to post its receives'
-    pending = {}
-    for ci, (a, b) in enumerate(spans):                # post every receive up front, in frame order per source
-        o = chunk_owner(ci, world)
-        if o != 0:
+    # Receives are posted in frame order (so they match the senders' order per source) but only a bounded window ahead of the
+    # chunk being linked: rank-0 memory stays at `window` record buffers however long the video is (a full-width buffer is
+    # chunk x (1 + 5 max_blobs) floats: 21 MB at the defaults, almost all of it padding).
+    window = max(4, 2 * world)
+    remote = [ci for ci in range(len(spans)) if chunk_owner(ci, world) != 0]
+    pending, nxt = {}, 0
+
+    def post_until(limit):
+        nonlocal nxt
+        while nxt < len(remote) and remote[nxt] < limit:
+            ci = remote[nxt]
+            a, b = spans[ci]
             buf = torch.empty((b - a, 1 + max_blobs * 5), dtype=torch.float32, device=device)
-            pending[ci] = (buf, dist.irecv(buf, src=o))
+            pending[ci] = (buf, dist.irecv(buf, src=chunk_owner(ci, world)))
+            nxt += 1
+
     for ci, (a, b) in enumerate(spans):
+        post_until(ci + window + 1)
         if ci in pending:
             buf, req = pending.pop(ci)
             req.wait()
