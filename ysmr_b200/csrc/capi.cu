@@ -387,6 +387,8 @@ int ysmr_set_gsff_gain(ysmr_ctx *c, int filter, int horizon, const double *h_gai
         if (g[n + k] != 0.0 || g[2 * n + k] != 0.0) c->lc.cross_zero = 0;
         if (g[k] != g[3 * n + k]) c->lc.xy_same = 0;      // (the fast linker loads one tap for both axes)
     }
+    if (filter < 3 && n <= 30)
+        for (int k = 0; k < n; ++k) c->lc.fast_gain[filter][k] = g[k];
     CU(c, cudaSetDevice(c->device));
     CU(c, cudaMemcpy(c->gain_dev[filter], g.data(), sizeof(double) * g.size(), cudaMemcpyHostToDevice));
     c->gain_set[filter] = true;

@@ -36,6 +36,8 @@ struct LinkConfig {
     const double *gain[LINK_MAX_FILTERS];
     int max_tracks, max_blobs;
     const double *exp_tab;               // np_exp_table_bits as 32 doubles (device memory)
+    double fast_gain[3][30];             // lane path: the x-row taps of filters 0..2 (horizons 10 / 20 / 30), as kernel
+                                         // PARAMETERS: a multiply-add takes a tap straight from the constant bank
     double grid_cell;                    // general path: cell size of the detection grid (pixels) ...
     int grid_w, grid_h;                  // ... and its extent, grid_w * grid_h <= LINK_GRID_CELLS
 };
