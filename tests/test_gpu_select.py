@@ -95,3 +95,36 @@ def test_select_scales_to_a_long_video():
     assert len(runs) == int(info[_lib.SI_GOOD_TRACKS])
     for r in runs:
         assert len(np.unique(tid[r])) == 1 and t[r[-1]] - t[r[0]] + 1 <= p.limit_frames
+
+
+def test_pipeline_selection_equals_the_reference_chain():
+    """frames -> GPU detect + link -> device-sorted rows -> GPU select_tracks, against
+    frames -> reference track_bacteria -> reference select_tracks (fixtures e2e_cfg1_300 / select_cfg1): the same tracks and
+    frames are selected, the selected rows carry the same values to the parity bars of the hot path."""
+    import pandas as pd
+    torch = pytest.importorskip('torch')
+    from ysmr_b200.api import Context
+    from ysmr_b200.select import select_tracks
+    from ysmr_b200.synth import SceneConfig, make_scene, render_frames
+    g = np.load(os.path.join(GOLDEN, 'e2e_cfg1_300.npz'))
+    d = np.load(os.path.join(GOLDEN, 'select_cfg1.npz'))
+    cfg = SceneConfig(**{k[6:]: g[k].item() for k in g.files if k.startswith('scene_')})
+    grey = render_frames(make_scene(cfg))
+    ctx = Context(cfg.height, cfg.width, 1, 0, max_batch=64, max_blobs=1024, max_tracks=1024)
+    ctx.archive_rows(True)
+    ctx.track_host(grey, 0, copy_rows=False)
+    rows = ctx.rows_sorted()                                   # (TRACK_ID, POSITION_T) order, from the device
+    ctx.close()
+    df = pd.DataFrame({'TRACK_ID': rows['track_id'].astype(np.uint32), 'POSITION_T': rows['frame'].astype(np.uint32),
+                       'POSITION_X': rows['x'], 'POSITION_Y': rows['y'], 'WIDTH': rows['w'].astype(np.float64),
+                       'HEIGHT': rows['h'].astype(np.float64), 'DEGREES_ANGLE': rows['deg'].astype(np.float64)})
+    out = select_tracks(path_to_file='cfg1_list.csv', df=df, results_directory='.', fps=float(d['fps']),
+                        frame_height=int(d['frame_height']), frame_width=int(d['frame_width']), settings=_settings(d))
+    assert out is not None
+    assert (out['TRACK_ID'].to_numpy() == d['sel_track']).all() and (out['POSITION_T'].to_numpy() == d['sel_t']).all()
+    assert (out['index'].to_numpy() == d['sel_index']).all()
+    ref = d['rows']
+    key = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(ref[:, 0], ref[:, 1]))}
+    take = [key[(int(a), int(b))] for a, b in zip(out['TRACK_ID'], out['POSITION_T'])]
+    assert np.abs(out[['POSITION_X', 'POSITION_Y']].to_numpy() - ref[take][:, 2:4]).max() < 1e-3
+    assert np.abs(out[['WIDTH', 'HEIGHT']].to_numpy() - ref[take][:, 4:6]).max() < 1e-3
