@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define YSMR_ABI_VERSION 4
+#define YSMR_ABI_VERSION 5
 
 enum {
     YSMR_OK = 0,
@@ -208,6 +208,26 @@ int ysmr_select_tracks(int device, int64_t n_rows, const uint32_t *h_track_id, c
                        const double *h_y, const double *h_w, const double *h_h, const ysmr_select_params *params,
                        uint8_t *h_good, int32_t *h_clean_index, int64_t *kick_reasons, double *info);
 const char *ysmr_select_last_error(void);
+
+/* ---- Per-track statistics (PARTIAL): the columns of evaluate_tracks()' df_stats that are reductions
+ * over a track's rows, /root/reference/ysmr/track_eval.py:905-945, 1030-1096.  Input: the selected rows (what select_tracks
+ * returns), grouped by track, HOST columns; h_track_start[n_tracks] = first row of every track.  median_kernel = the second
+ * median-filter size of `moving` (:933-940: round(fps), made odd).  Output h_stats[n_tracks][YSMR_STAT_COLUMNS] (HOST). */
+enum {
+    YSMR_STAT_DISTANCE = 0,       /* 'Distance (um)'  groupby sum of travelled_dist (pandas' Kahan sum)        (:1047) */
+    YSMR_STAT_SPEED = 1,          /* 'Speed (um/s)'   distance / time, 0 for tracks that never move            (:1052-1055) */
+    YSMR_STAT_TIME = 2,           /* 'Time (s)'       (last t_norm + 1) / fps                                   (:1046) */
+    YSMR_STAT_DISPLACEMENT = 3,   /* 'Displacement (um)'  largest pairwise distance, scipy pdist().max()       (:1031) */
+    YSMR_STAT_PERC_MOTILE = 4,    /* 'Perc. Motile'   sum of the twice median-filtered `moving` / frames * 100  (:1044-1045) */
+    YSMR_STAT_ACR = 5,            /* 'Arc-Chord Ratio'                                                           (:1048-1062) */
+    YSMR_STAT_BAC_LENGTH = 6,     /* 'Bacteria Length'  float32 mean of the float16 column bac_length          (:923, 1085) */
+    YSMR_STAT_DISPL_BY_LENGTH = 7,/* 'Displacement divided by length'                                           (:1086-1092) */
+    YSMR_STAT_COLUMNS = 8
+};
+int ysmr_track_statistics(int device, int64_t n_rows, const uint32_t *h_track_id, const uint32_t *h_t, const double *h_x,
+                          const double *h_y, const double *h_w, const double *h_h, double px_per_um, double fps, int median_kernel,
+                          const int32_t *h_track_start, int32_t n_tracks, double *h_stats);
+const char *ysmr_statistics_last_error(void);
 
 /* Development / measurement switches (not needed in production).  YSMR_OPT_FRONTEND_GEN: 4 (default) = the fused
  * bound-and-refine front-end kernel where it applies, 3 = always the three-kernel front-end of ABI 2 (bench.py's A/B

@@ -278,3 +278,22 @@ void emul_select_tracks(const int32_t *track_start, int n_tracks, int n_rows, co
 }
 
 }  // extern "C"
+
+#include "../../ysmr_b200/csrc/stats.cuh"
+
+extern "C" {
+
+// evaluate_tracks' per-track reductions (csrc/stats.cuh) for every track of a selected frame, single thread
+void emul_track_statistics(const int32_t *track_start, int n_tracks, int n_rows, const uint32_t *t, const double *x, const double *y,
+                           const double *w, const double *h, double px, double fps, int kernel2, double *out)
+{
+    StatCols c{t, x, y, w, h};
+    StatCfg g{px, fps, kernel2};
+    std::vector<uint8_t> ma(n_rows), mb(n_rows);
+    for (int k = 0; k < n_tracks; ++k) {
+        const int lo = track_start[k], hi = (k + 1 < n_tracks ? track_start[k + 1] : n_rows) - 1;
+        track_statistics_serial(c, g, lo, hi, ma.data(), mb.data(), out + (size_t)k * STAT_COLUMNS);
+    }
+}
+
+}  // extern "C"

@@ -21,7 +21,7 @@ def test_library_builds_loads_and_exports_the_header():
     for n in names:
         assert hasattr(lib, n), n
     assert set(names) == set(_lib.EXPORTS), set(names) ^ set(_lib.EXPORTS)
-    assert lib.ysmr_abi_version() == 4
+    assert lib.ysmr_abi_version() == 5
 
 
 def test_struct_layouts_match_header():

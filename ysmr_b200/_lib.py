@@ -93,6 +93,9 @@ EXPORTS = {
     'ysmr_select_tracks': (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                      C.POINTER(SelectParams), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'ysmr_select_last_error': (C.c_char_p, []),
+    'ysmr_track_statistics': (C.c_int, [C.c_int, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_int32, C.c_void_p]),
+    'ysmr_statistics_last_error': (C.c_char_p, []),
 }
 
 _lib = None
