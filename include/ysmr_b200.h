@@ -39,7 +39,8 @@ enum {
     YSMR_ST_BLOB_OVERFLOW = 2,     /* more external blobs in a frame than max_blobs */
     YSMR_ST_POINT_OVERFLOW = 4,    /* contour longer than the contour scratch pool allows */
     YSMR_ST_TRACK_OVERFLOW = 8,    /* more live tracks than max_tracks */
-    YSMR_ST_ROW_OVERFLOW = 16      /* rows_capacity of ysmr_link exceeded */
+    YSMR_ST_ROW_OVERFLOW = 16,     /* rows_capacity of ysmr_link exceeded */
+    YSMR_ST_GATE_TIMEOUT = 32      /* ysmr_track_*: a linker kernel waited ~10 s of SM clocks for its chunk's detections */
 };
 
 /* Threshold modes of the loop (track_eval.py:185, 198, 219). */

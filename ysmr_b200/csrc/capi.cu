@@ -594,7 +594,7 @@ int ysmr_status(ysmr_ctx *c, void *stream, int32_t *status_bits, int32_t *first_
         const int32_t reset[2] = {0, 0x7fffffff};
         CU(c, cudaMemcpy(&c->ctl->status, reset, sizeof(reset), cudaMemcpyHostToDevice));
         char buf[160];
-        snprintf(buf, sizeof(buf), "device status 0x%x at frame %d (1 runs, 2 blobs, 4 contour points, 8 tracks, 16 rows)",
+        snprintf(buf, sizeof(buf), "device status 0x%x at frame %d (1 runs, 2 blobs, 4 contour points, 8 tracks, 16 rows, 32 linker gate time-out)",
                  h.status, h.first_bad);
         c->err = buf;
         return YSMR_E_OVERFLOW;
