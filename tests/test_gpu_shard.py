@@ -119,3 +119,20 @@ def test_streamed_single_gpu_equals_pipeline():
                           lambda c, b, first: ctx.link(c, b, first, rows_capacity=int(c.numel()) * 512))
     ctx.close()
     assert np.concatenate(rows).tobytes() == _run_single(grey).tobytes()
+
+
+def test_two_devices_in_one_process():
+    """Kernel attributes (shared-memory opt-in of the linker and the fused front-end) are per device: a context on device 1
+    after one on device 0, in the same process, must work and give the same rows."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs 2 GPUs')
+    from ysmr_b200.api import Context
+    from ysmr_b200.synth import SceneConfig, make_scene, render_frames
+    cfg = SceneConfig(width=320, height=240, n_frames=40, n_cells=12, seed=3, margin=30.0)
+    grey = render_frames(make_scene(cfg))
+    rows = []
+    for dev in (0, 1):
+        ctx = Context(cfg.height, cfg.width, 1, dev, max_batch=16, max_blobs=512, max_tracks=512)
+        rows.append(ctx.track_host(grey, 0))
+        ctx.close()
+    assert rows[0].tobytes() == rows[1].tobytes() and len(rows[0]) > 0
