@@ -77,3 +77,46 @@ def test_select_params_follow_the_reference_conversions():
     assert p.max_empty == 1.05 and p.q_area == 0.1 and p.edge == 0.05 and p.max_recursion == 960
     st['exclude measurement when above x times average area'] = 0
     assert select_params(st, 30.0, 10, 10).area_factor == 0.0
+
+
+def test_select_tracks_host_side_frame_and_conventions(monkeypatch, tmp_path):
+    """The host half of the drop-in (ysmr_b200/select.py) without a GPU: with the C call replaced by the fixture's answer the
+    returned frame has the reference's columns, 'index' values and rows, the csv is written, and the None conventions hold."""
+    import pandas as pd
+    from ysmr_b200 import _lib, select
+    d = np.load(os.path.join(GOLDEN, 'select_cfg1.npz'))
+    rows = d['rows']
+    cols = ['TRACK_ID', 'POSITION_T', 'POSITION_X', 'POSITION_Y', 'WIDTH', 'HEIGHT', 'DEGREES_ANGLE']
+    df = pd.DataFrame({c: rows[:, i] for i, c in enumerate(cols)})
+    df['TRACK_ID'] = df['TRACK_ID'].astype(np.uint32); df['POSITION_T'] = df['POSITION_T'].astype(np.uint32)
+    # what the device would answer: rows of the cleaned-up frame are the input rows whose (track, t) survive
+    key = {(int(a), int(b)): i for i, (a, b) in enumerate(zip(rows[:, 0], rows[:, 1]))}
+    clean_rows = [key[(int(a), int(b))] for a, b in zip(d['clean_TRACK_ID'], d['clean_POSITION_T'])]
+    clean_index = np.full(len(rows), -1, np.int32); clean_index[clean_rows] = np.arange(len(clean_rows))
+    good = np.zeros(len(rows), np.uint8); good[np.asarray(clean_rows)[d['sel_index']]] = 1
+    state = {'status': _lib.SEL_OK}
+
+    def fake(track_id, t, x, y, w, h, params, device=0):
+        info = np.zeros(_lib.SELECT_INFO); info[_lib.SI_STATUS] = state['status']
+        info[_lib.SI_ROWS_BEFORE] = len(rows); info[_lib.SI_ROWS_AFTER] = len(clean_rows)
+        info[_lib.SI_TRACKS_BEFORE] = 60; info[_lib.SI_TRACKS_AFTER] = len(d['top_kick']); info[_lib.SI_GOOD_TRACKS] = 50
+        return good, clean_index, np.bincount(d['top_kick'], minlength=9).astype(np.int64), info
+    monkeypatch.setattr(select, 'select_rows', fake)
+    st = dict(zip([str(k) for k in d['setting_keys']], [float(v) for v in d['setting_values']]))
+    st['store processed .csv file'] = True
+    out = select.select_tracks(path_to_file=str(tmp_path / 'v_list.csv'), df=df, results_directory=str(tmp_path), fps=float(d['fps']),
+                               frame_height=int(d['frame_height']), frame_width=int(d['frame_width']), settings=st)
+    assert list(out.columns) == ['index'] + cols and (out['index'].to_numpy() == d['sel_index']).all()
+    assert (out['TRACK_ID'].to_numpy() == d['sel_track']).all() and (out['POSITION_T'].to_numpy() == d['sel_t']).all()
+    back = pd.read_csv(tmp_path / 'v_list_selected_data.csv')
+    assert list(back.columns) == ['index'] + cols and len(back) == len(out)
+    for status in (_lib.SEL_TOO_SHORT_BEFORE, _lib.SEL_TOO_SHORT_AFTER, _lib.SEL_NO_TRACKS):      # track_eval.py:599-606, 676-684, 816-819
+        state['status'] = status
+        assert select.select_tracks(path_to_file=str(tmp_path / 'v_list.csv'), df=df, results_directory=str(tmp_path), fps=30.0,
+                                    frame_height=922, frame_width=1228, settings=dict(st)) is None
+    state['status'] = _lib.SEL_OK
+    bad = dict(st); bad['pixel per micrometre'] = 0
+    assert select.select_tracks(path_to_file='x_list.csv', df=df, results_directory=str(tmp_path), fps=30.0, frame_height=922,
+                                frame_width=1228, settings=bad) is None
+    assert select.select_tracks(path_to_file='x_list.csv', df=df, results_directory=str(tmp_path), fps=0, frame_height=922,
+                                frame_width=1228, settings=dict(st, **{'frames per second': 0})) is None
