@@ -80,6 +80,15 @@ def analyse(path, settings=None, result_folder=None, return_df=False, **kwargs):
         df = select_tracks(path_to_file=path, df=df, results_directory=result_folder, settings=settings, **meta)
         if df is None:
             logger.warning('Error during video analysis of file {}.'.format(path))
+    else:
+        # an already selected file: the reference would go on to evaluate_tracks (main.py:130-138), which this repository
+        # does not replace -- the rows are handed back as they are
+        import pandas as pd
+        try:
+            df = pd.read_csv(path)
+        except Exception as ex:
+            logger.critical('Error reading data frame from file {}: {!r}'.format(path, ex))
+            df = None
     if settings.get('delete .csv file after analysis') and csv_file:
         try:
             os.remove(csv_file)
